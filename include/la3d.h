@@ -1,0 +1,157 @@
+/*
+ * la3d.h - C ABI of libla3d_sm100a.so, the B200 (sm_100a) implementation of
+ * LabelAny3D's per-object 3D box-fitting hot path.
+ *
+ * The reference is pure Python: its "plugin API" for this path is a handful of
+ * module-level functions.  Each entry point below names
+ * the reference function (path relative to the reference root, file:line) whose
+ * arithmetic it replaces; labelany3d_b200/dropin/{util,util_3dbox,cam_utils}.py
+ * re-create those functions, with the reference's signatures, on top of this
+ * ABI through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every array argument is a DEVICE pointer unless the comment says "host";
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as
+ *     void*) and returns 0 on success or a negative LA3D_E* code; the text of
+ *     the last failure on the calling thread is la3d_last_error();
+ *   - shapes are row-major (C order); images are [H][W], pixel (v,u) has flat
+ *     index p = v*W + u; a "plane" is one (image, instance) mask [H][W];
+ *   - nothing here allocates device memory: callers pass workspaces.
+ */
+#ifndef LA3D_H_
+#define LA3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LA3D_VERSION 100 /* 0.1.0 */
+
+typedef void* la3d_stream_t; /* cudaStream_t */
+
+/* error codes (return values) */
+#define LA3D_OK 0
+#define LA3D_EINVAL (-1) /* bad argument (null pointer, non-positive size, misaligned buffer) */
+#define LA3D_ECUDA (-2)  /* CUDA runtime error, see la3d_last_error() */
+#define LA3D_ENOMEM (-3) /* workspace too small */
+
+/* yaw estimators */
+#define LA3D_METHOD_PCA 0         /* src/util_3dbox.py:181-186 */
+#define LA3D_METHOD_CONVEX_HULL 1 /* src/util_3dbox.py:189-224 */
+#define LA3D_METHOD_SWEEP 2       /* new: uniform yaw sweep, SURVEY.md section 8 row a7 */
+
+/* per-box status written into the record (a GPU batch cannot raise per box) */
+#define LA3D_ST_OK 0
+#define LA3D_ST_NO_VALID 1      /* ValueError("No valid points after removing NaN values"), util_3dbox.py:142-143 */
+#define LA3D_ST_PCA_UNDEFINED 2 /* one point: scikit-learn PCA(2) refuses n_samples < 2 */
+#define LA3D_ST_BAD_METHOD 3    /* ValueError("Unknown method ..."), util_3dbox.py:151 */
+#define LA3D_ST_NONFINITE 4     /* +-inf left in the XZ footprint: scikit-learn's input check raises */
+#define LA3D_ST_TOO_MANY 5      /* la3d_fit_points only: more than 500 points and no sample_idx */
+
+/* the reference keeps at most this many points per box (util_3dbox.py:123-125) */
+#define LA3D_SUBSAMPLE 500
+
+/* packed box record: 64 scalars (float or double), SURVEY.md section 8e */
+#define LA3D_REC 64
+#define LA3D_O_VERT 0    /* 8x3 corners, camera frame            util_3dbox.py:165-169 */
+#define LA3D_O_CENTER 24 /* center_cam                           util_3dbox.py:172-173 */
+#define LA3D_O_DIM 27    /* [dz, dy, dx]                         util_3dbox.py:175     */
+#define LA3D_O_RCAM 30   /* R_cam row-major                      util_3dbox.py:176     */
+#define LA3D_O_YAW 39
+#define LA3D_O_NVALID 40 /* points that survived the NaN filter  util_3dbox.py:139-140 */
+#define LA3D_O_STATUS 41
+#define LA3D_O_UV 42     /* 8x2 projected corners                util.py:227-229       */
+#define LA3D_O_BOX2D 58  /* [min u, min v, max u, max v]         tools/combine_results.py:241-246 */
+#define LA3D_O_NMASK 62  /* pixels set in the mask / points given */
+#define LA3D_O_PAD 63
+
+int la3d_version(void);
+const char* la3d_last_error(void);
+
+/* ---------------------------------------------------------------------------
+ * depth -> camera-space points.  Replaces depth_to_points, src/util.py:52-75.
+ *   out[b][v][u][i] = sum_j R[i][j] * ( ((d*Kinv[i][0])*u + (d*Kinv[i][1])*v) + d*Kinv[i][2] ) + t[i]
+ * evaluated in float64 in the reference's operation order; `out_f64` selects a
+ * double (reference dtype) or float (rounded once from the double) output.
+ *   depth  [B][H][W] float
+ *   K      [B][9] (k_stride = 9) or one shared [9] (k_stride = 0), double.
+ *          k_is_inverse = 0: intrinsics, inverted on the device by LU with partial
+ *          pivoting (bit-identical to LAPACK for pinhole matrices);
+ *          k_is_inverse = 1: the caller already inverted them (np.linalg.inv).
+ *   R, t   nullable; [9] / [3] double shared by all images (the reference API
+ *          takes one R, t)
+ *   out    [B][H][W][3]
+ * ------------------------------------------------------------------------- */
+int la3d_depth_lift(const float* depth, const double* K, int k_stride, int k_is_inverse, const double* R,
+                    const double* t, int B, int H, int W, void* out, int out_f64, la3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Mask-stack scan.  Replaces the NumPy boolean-gather bookkeeping of pts[mask]
+ * (src/util.py:480-481 idiom; mask stack of src/util.py:382): one pass over the
+ * [B][I][H][W] byte masks produces, per plane, a bit mask (bit k of word w is
+ * pixel 32*w+k) and the number of set pixels in every 512-pixel chunk, which
+ * together locate the r-th set pixel in row-major order (= row r of pts[mask]).
+ *   masks         [B*I][H*W] uint8; nonzero = set (mask_is_01 = 1 promises 0/1 bytes,
+ *                 which is what numpy/torch bool arrays hold, and takes a shorter path)
+ *   bits          [B*I][la3d_words_per_plane(H,W)] uint32
+ *   chunk_counts  [B*I][la3d_chunks_per_plane(H,W)] uint16
+ * ------------------------------------------------------------------------- */
+size_t la3d_chunks_per_plane(int H, int W);
+size_t la3d_words_per_plane(int H, int W);
+int la3d_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
+                   uint16_t* chunk_counts, la3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Per-image subsample ranks.  Replaces `np.random.randint(0, N, 500)` of
+ * src/util_3dbox.py:123-125 for a whole batch: image b re-seeds NumPy's legacy
+ * MT19937 with (seed + image_offset + b) mod 2^32 and its instances draw from
+ * that stream in order, each only if its count N exceeds 500 (masked rejection
+ * on 32-bit draws, exactly RandomState.randint).
+ *   counts [B*I] int32  (out) set pixels per plane
+ *   ranks  [B*I][500] int32 (out) row indices into pts[mask]; untouched when N <= 500
+ * ------------------------------------------------------------------------- */
+int la3d_sample_ranks(const uint16_t* chunk_counts, int B, int I, int H, int W, uint32_t seed, uint32_t image_offset,
+                      int32_t* counts, int32_t* ranks, la3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Oriented box per (image, instance) from depth + scanned masks.  Replaces the
+ * composition depth_to_points -> pts[mask] -> estimate_bbox -> project_to_2d
+ * (src/util.py:52-75, src/util_3dbox.py:106-224, src/util.py:227-229,
+ * src/tools/combine_results.py:238-246) without materialising the point cloud.
+ *   depth [B][H][W] float; K [B][9] double intrinsics; ground nullable [B*I][3] double
+ *   bits / chunk_counts / counts / ranks: outputs of the two calls above
+ *   records [B*I][64] float (rec_f64 = 0) or double (rec_f64 = 1)
+ * ------------------------------------------------------------------------- */
+int la3d_fit_scanned(const float* depth, const double* K, const double* ground, const uint32_t* bits,
+                     const uint16_t* chunk_counts, const int32_t* counts, const int32_t* ranks, int B, int I, int H,
+                     int W, int method, int yaw_steps, void* records, int rec_f64, la3d_stream_t stream);
+
+/* The three calls above back to back.  `workspace` needs la3d_fit_workspace_bytes(). */
+size_t la3d_fit_workspace_bytes(int B, int I, int H, int W);
+int la3d_fit_boxes(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
+                   int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed, uint32_t image_offset,
+                   void* workspace, size_t workspace_bytes, void* records, int rec_f64, la3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Oriented box from explicit point sets.  Replaces estimate_bbox,
+ * src/util_3dbox.py:106-178, for the way the reference itself calls it (500
+ * points sampled from a mesh, src/util_3dbox.py:269-278).
+ *   pts        [total][3] double, box j owns rows offsets[j] .. offsets[j+1]-1
+ *   offsets    [nboxes+1] int64
+ *   sample_idx nullable [nboxes][500] int32: rows (relative to offsets[j]) to keep
+ *              when a box has more than 500 points (the caller draws them, e.g.
+ *              from np.random so the global stream advances as in the reference)
+ *   K          nullable [nboxes][9] double intrinsics for the 2D reprojection
+ *   ground     nullable [nboxes][3] double
+ * ------------------------------------------------------------------------- */
+int la3d_fit_points(const double* pts, const int64_t* offsets, const int32_t* sample_idx, const double* K,
+                    const double* ground, int nboxes, int method, int yaw_steps, void* records, int rec_f64,
+                    la3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LA3D_H_ */

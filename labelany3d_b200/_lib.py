@@ -1,0 +1,63 @@
+"""ctypes binding of ``libla3d_sm100a.so`` (the C ABI declared in ``include/la3d.h``).
+
+There is no CPU fallback: if the library is missing or a call fails, this raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_vp, _i, _u32, _sz = C.c_void_p, C.c_int, C.c_uint32, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/la3d.h one to one
+SIGNATURES = {
+    "la3d_version": (_i, []),
+    "la3d_last_error": (C.c_char_p, []),
+    "la3d_depth_lift": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "la3d_chunks_per_plane": (_sz, [_i, _i]),
+    "la3d_words_per_plane": (_sz, [_i, _i]),
+    "la3d_mask_scan": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "la3d_sample_ranks": (_i, [_vp, _i, _i, _i, _i, _u32, _u32, _vp, _vp, _vp]),
+    "la3d_fit_scanned": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "la3d_fit_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "la3d_fit_boxes": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _i, _vp]),
+    "la3d_fit_points": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+}
+
+_lib = None
+
+
+class La3dError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (once) and return the ctypes library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.isfile(path):
+        raise La3dError(
+            f"{path} is missing: build it with `python -m labelany3d_b200.build` "
+            "(needs nvcc; there is no CPU fallback for this path)")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().la3d_last_error().decode("utf-8", "replace")
+        raise La3dError(f"{what} failed with code {rc}: {msg}")

@@ -1,0 +1,216 @@
+"""Host side of the B200 box-fitting path: torch tensors in, torch tensors out.
+
+Every function here drives the hand-written sm_100a kernels of
+``libla3d_sm100a.so`` through the C ABI (``include/la3d.h``) with raw device
+pointers on the current CUDA stream.  torch is used for device memory and
+streams only.  Inputs must live on a CUDA device; nothing falls back to the CPU.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .records import METHODS, REC, SUBSAMPLE
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(name, t, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (this path has no CPU implementation)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _masks_u8(masks):
+    """bool -> (uint8 view, is_01=1); uint8 -> (as is, 0: any nonzero byte is 'set')."""
+    if masks.dtype == torch.bool:
+        return masks.view(torch.uint8), 1
+    if masks.dtype == torch.uint8:
+        return masks, 0
+    raise TypeError(f"masks must be bool or uint8, got {masks.dtype}")
+
+
+def _method_id(method):
+    # unknown names are passed through as an invalid id so the kernel reports
+    # LA3D_ST_BAD_METHOD per box, the way the reference raises per call
+    return METHODS.get(method, 99)
+
+
+# ---------------------------------------------------------------------------------------
+def depth_lift(depth, K, R=None, t=None, out_dtype=torch.float32, k_is_inverse=False):
+    """``depth[B,H,W]`` float32 -> camera-space points ``[B,H,W,3]``.
+
+    Batched form of the reference's ``depth_to_points`` (``src/util.py:52-75``).
+    ``K`` is ``[B,3,3]`` or one shared ``[3,3]`` (float64).  ``out_dtype=float64``
+    reproduces the reference's operation order bit for bit; ``float32`` is the
+    bandwidth-lean form (16 B per pixel), rounded once from the float64 value.
+    """
+    lib = _lib.load()
+    depth = _need_cuda("depth", depth, torch.float32)
+    B, H, W = depth.shape
+    K = _need_cuda("K", K, torch.float64)
+    if K.shape == (3, 3):
+        k_stride = 0
+    elif K.shape == (B, 3, 3):
+        k_stride = 9
+    else:
+        raise ValueError(f"K must be [3,3] or [{B},3,3], got {tuple(K.shape)}")
+    if R is not None:
+        R = _need_cuda("R", R, torch.float64)
+        assert R.shape == (3, 3)
+    if t is not None:
+        t = _need_cuda("t", t, torch.float64)
+        assert t.shape == (3,)
+    if out_dtype not in (torch.float32, torch.float64):
+        raise TypeError("out_dtype must be float32 or float64")
+    out = torch.empty((B, H, W, 3), dtype=out_dtype, device=depth.device)
+    with torch.cuda.device(depth.device):
+        rc = lib.la3d_depth_lift(_ptr(depth), _ptr(K), k_stride, int(bool(k_is_inverse)), _ptr(R), _ptr(t), B, H, W,
+                                 _ptr(out), int(out_dtype == torch.float64), _stream())
+    _lib.check(rc, "la3d_depth_lift")
+    return out
+
+
+def scan_layout(H, W):
+    """(chunks per plane, bit-words per plane) of the mask scan for an ``H x W`` image."""
+    lib = _lib.load()
+    return int(lib.la3d_chunks_per_plane(H, W)), int(lib.la3d_words_per_plane(H, W))
+
+
+def mask_scan(masks):
+    """``masks[..., H, W]`` (bool / uint8) -> ``(bits[P, words] int32, chunk_counts[P, chunks] int16)``.
+
+    ``P`` = product of the leading dimensions.  Bit ``k`` of word ``w`` of a plane is
+    pixel ``32 w + k`` in row-major order; ``chunk_counts`` holds the set pixels of every
+    512-pixel chunk (as unsigned 16-bit values stored in an int16 tensor).
+    """
+    lib = _lib.load()
+    masks = _need_cuda("masks", masks)
+    m8, is01 = _masks_u8(masks)
+    H, W = masks.shape[-2:]
+    planes = masks.numel() // (H * W)
+    chunks, words = scan_layout(H, W)
+    bits = torch.empty((planes, words), dtype=torch.int32, device=masks.device)
+    cc = torch.empty((planes, chunks), dtype=torch.int16, device=masks.device)
+    with torch.cuda.device(masks.device):
+        rc = lib.la3d_mask_scan(_ptr(m8), planes, H, W, is01, _ptr(bits), _ptr(cc), _stream())
+    _lib.check(rc, "la3d_mask_scan")
+    return bits, cc
+
+
+def sample_ranks(chunk_counts, B, I, H, W, seed=0, image_offset=0):
+    """Per-plane pixel counts and the reference's 500 random rows of ``pts[mask]``.
+
+    Returns ``(counts[B,I] int32, ranks[B,I,500] int32)``; ``ranks`` of planes with at
+    most 500 pixels are left at -1 (the reference keeps all their points).
+    """
+    lib = _lib.load()
+    cc = _need_cuda("chunk_counts", chunk_counts, torch.int16)
+    counts = torch.empty((B, I), dtype=torch.int32, device=cc.device)
+    ranks = torch.full((B, I, SUBSAMPLE), -1, dtype=torch.int32, device=cc.device)
+    with torch.cuda.device(cc.device):
+        rc = lib.la3d_sample_ranks(_ptr(cc), B, I, H, W, int(seed) & 0xFFFFFFFF, int(image_offset) & 0xFFFFFFFF,
+                                   _ptr(counts), _ptr(ranks), _stream())
+    _lib.check(rc, "la3d_sample_ranks")
+    return counts, ranks
+
+
+class BoxFitter:
+    """Reusable plan for ``fit_boxes`` on a fixed shape: owns the workspace and the output.
+
+    One call = three kernels on the current stream (mask scan, subsample ranks, fit);
+    nothing is allocated and nothing synchronises.
+    """
+
+    def __init__(self, B, I, H, W, device="cuda", out_dtype=torch.float64):
+        self.lib = _lib.load()
+        self.shape = (int(B), int(I), int(H), int(W))
+        self.device = torch.device(device)
+        if out_dtype not in (torch.float32, torch.float64):
+            raise TypeError("out_dtype must be float32 or float64")
+        self.out_dtype = out_dtype
+        self.ws_bytes = int(self.lib.la3d_fit_workspace_bytes(*self.shape))
+        self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        assert self.workspace.data_ptr() % 256 == 0
+        self.records = torch.empty((B, I, REC), dtype=out_dtype, device=self.device)
+
+    def __call__(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0, out=None):
+        B, I, H, W = self.shape
+        depth = _need_cuda("depth", depth, torch.float32)
+        K = _need_cuda("K", K, torch.float64)
+        masks = _need_cuda("masks", masks)
+        if tuple(depth.shape) != (B, H, W) or tuple(masks.shape) != (B, I, H, W) or tuple(K.shape) != (B, 3, 3):
+            raise ValueError(f"shapes do not match the plan {self.shape}: depth {tuple(depth.shape)}, "
+                             f"masks {tuple(masks.shape)}, K {tuple(K.shape)}")
+        if ground is not None:
+            ground = _need_cuda("ground", ground, torch.float64)
+            if tuple(ground.shape) != (B, I, 3):
+                raise ValueError(f"ground must be [{B},{I},3]")
+        m8, is01 = _masks_u8(masks)
+        rec = self.records if out is None else _need_cuda("out", out, self.out_dtype)
+        with torch.cuda.device(self.device):
+            rc = self.lib.la3d_fit_boxes(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01,
+                                         _method_id(method), int(yaw_steps), int(seed) & 0xFFFFFFFF,
+                                         int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace), self.ws_bytes,
+                                         _ptr(rec), int(self.out_dtype == torch.float64), _stream())
+        _lib.check(rc, "la3d_fit_boxes")
+        return rec
+
+
+def fit_boxes(depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0,
+              out_dtype=torch.float64):
+    """``depth[B,H,W], K[B,3,3], masks[B,I,H,W], ground[B,I,3]|None`` -> records ``[B,I,64]``.
+
+    The composed path of SURVEY.md section 3.4 for a batch: per instance the
+    reference's ``estimate_bbox`` applied to ``depth_to_points(depth)[mask]`` plus the
+    2D reprojection of the corners, with the legacy NumPy RNG re-seeded to
+    ``seed + image_offset + b`` at the start of image ``b``.
+    """
+    B, I, H, W = masks.shape
+    return BoxFitter(B, I, H, W, device=depth.device, out_dtype=out_dtype)(
+        depth, K, masks, ground, method, yaw_steps, seed, image_offset).clone()
+
+
+def fit_points(points, offsets, sample_idx=None, K=None, ground=None, method="pca", yaw_steps=0,
+               out_dtype=torch.float64):
+    """Boxes from explicit point sets (the reference's own way of calling ``estimate_bbox``).
+
+    ``points[total,3]`` float64, ``offsets[n+1]`` int64, ``sample_idx[n,500]`` int32 (rows to
+    keep for sets with more than 500 points), ``K[n,3,3]`` / ``ground[n,3]`` float64 or None.
+    """
+    lib = _lib.load()
+    points = _need_cuda("points", points, torch.float64)
+    offsets = _need_cuda("offsets", offsets, torch.int64)
+    n = offsets.numel() - 1
+    if sample_idx is not None:
+        sample_idx = _need_cuda("sample_idx", sample_idx, torch.int32)
+        assert tuple(sample_idx.shape) == (n, SUBSAMPLE)
+    if K is not None:
+        K = _need_cuda("K", K, torch.float64)
+        assert tuple(K.shape) == (n, 3, 3)
+    if ground is not None:
+        ground = _need_cuda("ground", ground, torch.float64)
+        assert tuple(ground.shape) == (n, 3)
+    rec = torch.empty((n, REC), dtype=out_dtype, device=points.device)
+    with torch.cuda.device(points.device):
+        rc = lib.la3d_fit_points(_ptr(points), _ptr(offsets), _ptr(sample_idx), _ptr(K), _ptr(ground), n,
+                                 _method_id(method), int(yaw_steps), _ptr(rec), int(out_dtype == torch.float64),
+                                 _stream())
+    _lib.check(rc, "la3d_fit_points")
+    return rec
+
+
+def to_numpy(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
