@@ -151,6 +151,15 @@ int la3d_fit_points(const double* pts, const int64_t* offsets, const int32_t* sa
                     const double* ground, int nboxes, int method, int yaw_steps, void* records, int rec_f64,
                     la3d_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Pinhole projection of explicit points.  Replaces project_to_2d,
+ * src/util.py:227-229 (= src/tools/combine_results.py:105-108): [u,v] = (K p)[:2] / (K p)[2].
+ *   pts [n][3] double; K [m][9] double; k_index nullable [n] int32 (which K each point uses;
+ *   null = all use K[0]); uv [n][2] double (out)
+ * ------------------------------------------------------------------------- */
+int la3d_project_points(const double* pts, const double* K, const int32_t* k_index, long long n, double* uv,
+                        la3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,7 @@ SIGNATURES = {
     "la3d_fit_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "la3d_fit_boxes": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _i, _vp]),
     "la3d_fit_points": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "la3d_project_points": (_i, [_vp, _vp, _vp, C.c_longlong, _vp, _vp]),
 }
 
 _lib = None

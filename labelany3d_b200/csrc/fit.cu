@@ -389,8 +389,8 @@ __global__ void __launch_bounds__(kThreads) fit_kernel(FitArgs a) {
   const bool subsample = n_src > LA3D_SUBSAMPLE;
   int status = LA3D_ST_OK;
   if (!kScanned && subsample && !a.sample_idx) status = LA3D_ST_TOO_MANY;
-  if (a.method != LA3D_METHOD_PCA && a.method != LA3D_METHOD_CONVEX_HULL && a.method != LA3D_METHOD_SWEEP)
-    status = LA3D_ST_BAD_METHOD;
+  const bool bad_method =
+      a.method != LA3D_METHOD_PCA && a.method != LA3D_METHOD_CONVEX_HULL && a.method != LA3D_METHOD_SWEEP;
   const int nsel = status ? 0 : (int)min((long long)LA3D_SUBSAMPLE, n_src);
 
   // ---- gather + lift + ground alignment + NaN-row filter ---------------------------
@@ -426,7 +426,9 @@ __global__ void __launch_bounds__(kThreads) fit_kernel(FitArgs a) {
     n_valid = r[0]; inf_xz = r[1]; inf_y = r[2];
   }
   if (status == LA3D_ST_OK) {
+    // same order as the reference: the NaN filter raises first (:142-143), then the method check (:151)
     if (n_valid == 0) status = LA3D_ST_NO_VALID;
+    else if (bad_method) status = LA3D_ST_BAD_METHOD;
     else if (inf_xz) status = LA3D_ST_NONFINITE;      // scikit-learn's input check raises; Qhull fails first and falls back to it
     else if (n_valid == 1 && a.method != LA3D_METHOD_SWEEP) status = LA3D_ST_PCA_UNDEFINED;   // PCA(2) needs 2 samples
   }

@@ -1,0 +1,80 @@
+"""Drop-in for the three hot-path functions of the reference's ``src/util.py``:
+``depth_to_points`` (``:52-75``), ``project_to_2d`` (``:227-229``) and ``draw_cube``
+(``:232-289``).  Same names, signatures and return types; the arithmetic runs on the B200.
+
+Only these three are provided: the rest of the reference's ``util.py`` is model / IO glue
+outside this path.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from labelany3d_b200 import ops as _ops
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("labelany3d_b200 needs a CUDA device: this path has no CPU implementation")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def depth_to_points(depth, K=None, R=None, t=None):
+    """``depth[bs,H,W]`` -> points ``[H,W,3]`` float64 of batch element 0, like the reference.
+
+    ``K`` is required (the reference fails on ``np.linalg.inv(None)`` too).  The intrinsics are
+    inverted on the host with ``np.linalg.inv`` exactly as the reference does and the kernel then
+    evaluates the reference's operation order in float64, so for ``K``-only calls (the pipeline's
+    use, ``src/batch_scripts/depth.py:154``) the result is bit-identical to NumPy's.
+    """
+    Kinv = np.linalg.inv(K)            # raises like the reference for K=None / singular K
+    dev = _device()
+    d = depth.detach() if isinstance(depth, torch.Tensor) else torch.as_tensor(np.asarray(depth))
+    if d.dim() != 3:
+        raise ValueError(f"expected depth of shape [bs,H,W], got {tuple(d.shape)}")
+    d0 = d[:1].to(device=dev, dtype=torch.float32).contiguous()      # only element 0 is returned
+    Rd = None if R is None else torch.as_tensor(np.asarray(R, dtype=np.float64).copy(), device=dev)
+    td = None if t is None else torch.as_tensor(np.asarray(t, dtype=np.float64).copy(), device=dev)
+    out = _ops.depth_lift(d0, torch.as_tensor(np.ascontiguousarray(Kinv, dtype=np.float64), device=dev), Rd, td,
+                          out_dtype=torch.float64, k_is_inverse=True)
+    return out[0].cpu().numpy()
+
+
+def project_to_2d(point_3d, camera_matrix):
+    """``[u,v] = (K p)[:2] / (K p)[2]`` for one point ``[3]`` (reference API) or many ``[n,3]``."""
+    dev = _device()
+    p = np.asarray(point_3d, dtype=np.float64)
+    single = p.ndim == 1
+    uv = _ops.project_points(torch.as_tensor(np.ascontiguousarray(p.reshape(-1, 3)), device=dev),
+                             torch.as_tensor(np.ascontiguousarray(camera_matrix, dtype=np.float64), device=dev))
+    uv = uv.cpu().numpy()
+    return uv[0] if single else uv
+
+
+def draw_cube(scene_dir, is_ground=False):
+    """Draw the scene's boxes over ``input.png`` (``src/util.py:232-289``); drawing stays on the
+    host with OpenCV like the reference, the corner projection of ALL boxes is one kernel launch."""
+    import cv2
+    from PIL import Image
+    with open(os.path.join(scene_dir, "cam_params.json")) as f:
+        K = np.array(json.load(f)["K"])
+    with open(os.path.join(scene_dir, "3dbbox_ground.json" if is_ground else "3dbbox.json")) as f:
+        cubes = json.load(f)
+    image = cv2.cvtColor(np.array(Image.open(os.path.join(scene_dir, "input.png"))), cv2.COLOR_RGB2BGR)
+    if cubes:
+        corners = np.array([c["bbox3D_cam"] for c in cubes], dtype=np.float64).reshape(-1, 3)
+        all_uv = project_to_2d(corners, K).reshape(len(cubes), 8, 2)
+    edges = [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]
+    for cube, uv in zip(cubes, all_uv if cubes else []):
+        top = int(np.argmin(uv[:, 1]))          # first minimum, like the reference's scan
+        for p in uv:
+            cv2.circle(image, tuple(np.round(p).astype(int)), radius=3, color=(0, 255, 0), thickness=-1)
+        for a, b in edges:
+            cv2.line(image, tuple(np.round(uv[a]).astype(int)), tuple(np.round(uv[b]).astype(int)), (255, 0, 0), 2)
+        cv2.putText(image, f'{cube["category_name"]}', (int(uv[top][0]), int(uv[top][1]) - 10),
+                    cv2.FONT_HERSHEY_SIMPLEX, 0.5, (0, 0, 255), 1)
+    cv2.imwrite(os.path.join(scene_dir, "vis_3dbox.png" if is_ground else "vis_3dbox_no_ground.png"), image)

@@ -146,7 +146,11 @@ class BoxFitter:
         assert self.workspace.data_ptr() % 256 == 0
         self.records = torch.empty((B, I, REC), dtype=out_dtype, device=self.device)
 
-    def __call__(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0, out=None):
+    def __call__(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0, out=None,
+                 events=None):
+        """Fit every (image, instance) box; returns ``records[B,I,64]`` (a buffer owned by the plan
+        unless ``out`` is given).  ``events``: optional list of 4 ``torch.cuda.Event`` recorded before
+        the scan, between the kernels and after the fit (per-kernel timing without a profiler)."""
         B, I, H, W = self.shape
         depth = _need_cuda("depth", depth, torch.float32)
         K = _need_cuda("K", K, torch.float64)
@@ -160,13 +164,44 @@ class BoxFitter:
                 raise ValueError(f"ground must be [{B},{I},3]")
         m8, is01 = _masks_u8(masks)
         rec = self.records if out is None else _need_cuda("out", out, self.out_dtype)
+        if tuple(rec.shape) != (B, I, REC):
+            raise ValueError(f"out must be [{B},{I},{REC}]")
+        f64 = int(self.out_dtype == torch.float64)
+        lib = self.lib
         with torch.cuda.device(self.device):
-            rc = self.lib.la3d_fit_boxes(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01,
-                                         _method_id(method), int(yaw_steps), int(seed) & 0xFFFFFFFF,
-                                         int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace), self.ws_bytes,
-                                         _ptr(rec), int(self.out_dtype == torch.float64), _stream())
-        _lib.check(rc, "la3d_fit_boxes")
+            st = _stream()
+            if events is None:
+                rc = lib.la3d_fit_boxes(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01,
+                                        _method_id(method), int(yaw_steps), int(seed) & 0xFFFFFFFF,
+                                        int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace), self.ws_bytes,
+                                        _ptr(rec), f64, st)
+                _lib.check(rc, "la3d_fit_boxes")
+            else:
+                # the same three kernels through the step-wise entry points, with events in between
+                bits, cc, counts, ranks = self._carve()
+                events[0].record()
+                _lib.check(lib.la3d_mask_scan(_ptr(m8), B * I, H, W, is01, bits, cc, st), "la3d_mask_scan")
+                events[1].record()
+                _lib.check(lib.la3d_sample_ranks(cc, B, I, H, W, int(seed) & 0xFFFFFFFF,
+                                                 int(image_offset) & 0xFFFFFFFF, counts, ranks, st), "la3d_sample_ranks")
+                events[2].record()
+                _lib.check(lib.la3d_fit_scanned(_ptr(depth), _ptr(K), _ptr(ground), bits, cc, counts, ranks, B, I, H, W,
+                                                _method_id(method), int(yaw_steps), _ptr(rec), f64, st), "la3d_fit_scanned")
+                events[3].record()
         return rec
+
+    def _carve(self):
+        """Workspace sub-buffers in the order ``la3d_fit_boxes`` lays them out (256-byte aligned)."""
+        B, I, H, W = self.shape
+        planes = B * I
+        chunks, words = scan_layout(H, W)
+        up = lambda v: (v + 255) & ~255  # noqa: E731
+        base = self.workspace.data_ptr()
+        o_cc = up(planes * words * 4)
+        o_counts = up(o_cc + planes * chunks * 2)
+        o_ranks = up(o_counts + planes * 4)
+        assert up(o_ranks + planes * SUBSAMPLE * 4) == self.ws_bytes
+        return base, base + o_cc, base + o_counts, base + o_ranks
 
 
 def fit_boxes(depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0,
@@ -210,6 +245,22 @@ def fit_points(points, offsets, sample_idx=None, K=None, ground=None, method="pc
                                  _stream())
     _lib.check(rc, "la3d_fit_points")
     return rec
+
+
+def project_points(points, K, k_index=None):
+    """``points[n,3]`` float64, ``K[m,3,3]`` (or ``[3,3]``) -> ``uv[n,2]``: the reference's ``project_to_2d``
+    (``src/util.py:227-229``) for a batch; ``k_index[n]`` int32 picks the intrinsics of each point."""
+    lib = _lib.load()
+    points = _need_cuda("points", points, torch.float64)
+    K = _need_cuda("K", K, torch.float64)
+    n = points.shape[0]
+    if k_index is not None:
+        k_index = _need_cuda("k_index", k_index, torch.int32)
+    uv = torch.empty((n, 2), dtype=torch.float64, device=points.device)
+    with torch.cuda.device(points.device):
+        rc = lib.la3d_project_points(_ptr(points), _ptr(K), _ptr(k_index), n, _ptr(uv), _stream())
+    _lib.check(rc, "la3d_project_points")
+    return uv
 
 
 def to_numpy(t):

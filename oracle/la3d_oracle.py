@@ -522,8 +522,6 @@ def fit_points_record(pc, K, ground=None, method="pca", yaw_steps=None, rng=None
     """One box record from a point set (the mesh-points entry of the reference)."""
     pc = np.asarray(pc)
     n_mask = pc.shape[0]
-    if method not in ("pca", "convex_hull", "sweep"):
-        return failed_record(ST_BAD_METHOD, 0, n_mask)
     try:
         with np.errstate(invalid="ignore", over="ignore", divide="ignore"):
             d = fit_details(pc, ground, method, yaw_steps, rng=rng, impl=impl, sample_idx=sample_idx)

@@ -291,6 +291,80 @@ def main():
                 sel[[orc.O_YAW, orc.O_NVALID]] = False    # not observable through the reference API
                 track(f"scene[{method},{impl}]", mine[..., sel], rec[..., sel])
 
+    # ---------------------------------------------------------------- cam_utils helpers
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_la3d_ref_cam", os.path.join(live_reference.REF_SRC, "cam_utils.py"))
+    cam = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cam)
+    orbit_args = [(10.0, 20.0, 1.0, 1, 1), (-30.0, 140.0, 2.5, 1, 0), (0.3, -1.2, 1.0, 0, 1), (0.0, 0.0, 1.0, 1, 0)]
+    put("cam/orbit_args", np.array(orbit_args))
+    put("cam/orbit", np.stack([cam.orbit_camera(e, a, r, bool(d), None, bool(o)) for e, a, r, d, o in orbit_args]))
+    tgt = np.array([0.5, -0.25, 1.0], dtype=np.float32)
+    put("cam/orbit_target", np.stack([cam.orbit_camera(e, a, r, bool(d), tgt, bool(o)) for e, a, r, d, o in orbit_args]))
+    vv = rng.normal(size=(5, 3))
+    put("cam/vecs", vv)
+    put("cam/length", cam.length(vv))
+    put("cam/safe_normalize", cam.safe_normalize(vv))
+
+    # ---------------------------------------------------------------- scene driver (a9) + draw_cube (a10)
+    # trimesh is absent from this image: the reference's driver runs unmodified against a
+    # stand-in that serves pre-sampled points, so its directory / JSON logic is pinned too.
+    import json
+    import tempfile
+    import types
+    import cv2
+    scene = tempfile.mkdtemp()
+    os.makedirs(os.path.join(scene, "reconstruction"))
+    objs = [("0", "chair", 500), ("1", "dining_table", 500), ("2", "bad", 0), ("3", "cup", 500)]
+    srng = np.random.RandomState(99)
+    clouds = {}
+    for oid, cat, n in objs:
+        name = f"{oid}_{cat}"
+        open(os.path.join(scene, "reconstruction", name + ".glb"), "w").close()
+        clouds[name] = cloud(srng, n, center=(srng.uniform(-1, 1), 0.2, srng.uniform(3, 6)), yaw=srng.uniform(-2, 2)) if n else None
+        up = np.array([srng.normal() * 0.1, -1.0 + srng.normal() * 0.05, srng.normal() * 0.1, 0.0]) * 1.7
+        np.save(os.path.join(scene, "reconstruction", name + "_canonical_upright.npy"), up)
+        put(f"driver/{name}/points", np.zeros((0, 3)) if clouds[name] is None else clouds[name])
+        put(f"driver/{name}/upright", up)
+    open(os.path.join(scene, "reconstruction", "full_scene.glb"), "w").close()
+    put("driver/names", np.array([f"{o}_{c}" for o, c, _ in objs]))
+
+    class FakeMesh:
+        def __init__(self, pts):
+            self.pts = pts
+            self.is_empty = pts is None
+            self.area = 0.0 if pts is None else 1.0
+            self.faces = [] if pts is None else [0]
+
+        def sample(self, n):
+            assert n == 500
+            return self.pts
+
+    fake = types.ModuleType("trimesh")
+    fake.Scene = type("Scene", (), {})
+    fake.load = lambda path: FakeMesh(clouds[os.path.basename(path)[:-4]])
+    fake.points = types.SimpleNamespace(PointCloud=lambda p: types.SimpleNamespace(vertices=p))
+    box.trimesh = fake
+    for method in ("pca", "convex_hull"):
+        with live_reference.quiet():
+            lst = box.save_3d_with_ground_alignment_bbox(scene, method)
+        with open(os.path.join(scene, "3dbbox_ground.json")) as f:
+            assert json.load(f) == lst
+        put(f"driver/json_{method}", np.array(json.dumps(lst)))
+    # draw_cube on the pca boxes
+    Wd, Hd = 160, 120
+    Kd = np.array([[0.9 * Wd, 0, Wd / 2], [0, 0.9 * Wd, Hd / 2], [0, 0, 1.0]])
+    with open(os.path.join(scene, "cam_params.json"), "w") as f:
+        json.dump({"K": Kd.tolist(), "H": Hd, "W": Wd}, f)
+    img = (np.random.RandomState(5).rand(Hd, Wd, 3) * 255).astype(np.uint8)
+    cv2.imwrite(os.path.join(scene, "input.png"), cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+    with live_reference.quiet():
+        box.save_3d_with_ground_alignment_bbox(scene, "pca")
+    util.draw_cube(scene, is_ground=True)
+    put("driver/K", Kd)
+    put("driver/input_rgb", img)
+    put("driver/vis_bgr", cv2.imread(os.path.join(scene, "vis_3dbox.png")))
+
     out = os.path.join(HERE, "golden_v1.npz")
     np.savez_compressed(out, **G)
     print(f"wrote {out}: {len(G)} arrays, {os.path.getsize(out) / 1024:.1f} KiB")

@@ -1,0 +1,149 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the
+header declares, the host helpers reproduce the reference's values, and the product never imports
+the oracle.  No compute call is made on the GPU here."""
+
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+import labelany3d_b200
+from labelany3d_b200 import _lib, build, records
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    path = labelany3d_b200.dropin_path()
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    for name in ("util", "util_3dbox", "cam_utils"):
+        sys.modules.pop(name, None)
+    import cam_utils
+    import util
+    import util_3dbox
+    assert util_3dbox.__file__.startswith(path)
+    return util, util_3dbox, cam_utils
+
+
+def test_library_exports_every_header_symbol():
+    path = build.build()
+    assert os.path.isfile(path)
+    header = open(os.path.join(ROOT, "include", "la3d.h")).read()
+    declared = set(re.findall(r"\b(la3d_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().la3d_version() == 100
+    # layout helpers are pure host functions
+    assert _lib.load().la3d_chunks_per_plane(480, 640) == 600
+    assert _lib.load().la3d_words_per_plane(480, 640) == 9600
+    assert _lib.load().la3d_chunks_per_plane(7, 13) == 1
+    assert _lib.load().la3d_fit_workspace_bytes(256, 8, 480, 640) > 256 * 8 * 9600 * 4
+
+
+def test_record_layout_matches_header_and_oracle():
+    from oracle import la3d_oracle as orc
+    header = open(os.path.join(ROOT, "include", "la3d.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define LA3D_(O_[A-Z0-9]+|REC|ST_[A-Z_]+|SUBSAMPLE|METHOD_[A-Z_]+)\s+(-?\d+)", header)}
+    for name in ("O_VERT", "O_CENTER", "O_DIM", "O_RCAM", "O_YAW", "O_NVALID", "O_STATUS", "O_UV", "O_BOX2D", "O_NMASK",
+                 "O_PAD", "REC", "ST_OK", "ST_NO_VALID", "ST_PCA_UNDEFINED", "ST_BAD_METHOD", "ST_NONFINITE", "SUBSAMPLE"):
+        assert defs[name] == getattr(records, name) == getattr(orc, name), name
+    assert records.METHODS == {"pca": defs["METHOD_PCA"], "convex_hull": defs["METHOD_CONVEX_HULL"],
+                               "sweep": defs["METHOD_SWEEP"]}
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "labelany3d_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), os.path.join(dirpath, f)
+                assert "la3d_oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(build, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.La3dError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_cpu_tensors_are_rejected():
+    import torch
+    from labelany3d_b200 import ops
+    with pytest.raises(TypeError, match="CUDA tensor"):
+        ops.depth_lift(torch.zeros(1, 4, 4), torch.eye(3, dtype=torch.float64))
+    with pytest.raises(TypeError, match="CUDA tensor"):
+        ops.mask_scan(torch.zeros(1, 1, 4, 4, dtype=torch.bool))
+
+
+def test_status_errors_carry_the_reference_messages(golden):
+    assert str(records.status_error(records.ST_NO_VALID)) == str(golden["errors/all_nan"]).split(": ", 1)[1]
+    assert str(records.status_error(records.ST_BAD_METHOD, "nope")) == str(golden["errors/bad_method"]).split(": ", 1)[1]
+    assert str(records.status_error(records.ST_PCA_UNDEFINED, n_valid=1)) == str(golden["errors/one_point"]).split(": ", 1)[1]
+    assert records.status_error(records.ST_OK) is None
+    assert records.bbox2d_trunc([-5.0, 3.0, 700.0, 500.0], 640, 480) == [0, 3.0, 640, 480]
+
+
+def test_geometry_helpers(dropin, golden):
+    _, box, _ = dropin
+    for y, ref in zip(golden["helpers/yaws"], golden["helpers/rotate_y"]):
+        np.testing.assert_array_equal(box.rotate_y(y), ref)
+    for (a, b), ref, nrm in zip(golden["helpers/vec_pairs"], golden["helpers/rotation_from_vectors"],
+                                golden["helpers/normalize"]):
+        np.testing.assert_array_equal(box.rotation_matrix_from_vectors(a, b), ref)
+        np.testing.assert_array_equal(box.normalize(a), nrm)
+    assert box.normalize(np.zeros(3)).tolist() == [0, 0, 0]
+    for p, ref in zip(golden["helpers/box_params"], golden["helpers/box_vertices"]):
+        np.testing.assert_array_equal(box.convert_box_vertices(*p), ref)
+    for p, ref in zip(golden["helpers/plane_args"], golden["helpers/plane_dist"]):
+        assert box.point_to_plane_distance(p[:4], p[4], p[5], p[6]) == ref
+
+
+def test_cam_utils(dropin, golden):
+    _, _, cam = dropin
+    tgt = np.array([0.5, -0.25, 1.0], dtype=np.float32)
+    for (e, a, r, d, o), ref, ref_t in zip(golden["cam/orbit_args"], golden["cam/orbit"], golden["cam/orbit_target"]):
+        np.testing.assert_array_equal(cam.orbit_camera(e, a, r, bool(d), None, bool(o)), ref)
+        np.testing.assert_array_equal(cam.orbit_camera(e, a, r, bool(d), tgt, bool(o)), ref_t)
+    np.testing.assert_array_equal(cam.length(golden["cam/vecs"]), golden["cam/length"])
+    np.testing.assert_array_equal(cam.safe_normalize(golden["cam/vecs"]), golden["cam/safe_normalize"])
+    import torch
+    v = torch.as_tensor(golden["cam/vecs"])
+    np.testing.assert_allclose(cam.length(v).numpy(), golden["cam/length"], rtol=1e-15)   # reference's torch branch is broken
+    assert cam.depth_to_points is dropin[0].depth_to_points
+
+
+def test_signatures_match_the_reference(dropin):
+    import inspect
+    util, box, cam = dropin
+    want = {
+        (util, "depth_to_points"): "(depth, K=None, R=None, t=None)",
+        (util, "project_to_2d"): "(point_3d, camera_matrix)",
+        (util, "draw_cube"): "(scene_dir, is_ground=False)",
+        (box, "normalize"): "(v)",
+        (box, "rotate_y"): "(yaw)",
+        (box, "rotation_matrix_from_vectors"): "(vec1, vec2)",
+        (box, "point_to_plane_distance"): "(plane, x, y, z)",
+        (box, "convert_box_vertices"): "(center_x, center_y, center_z, l, w, h, yaw)",
+        (box, "_estimate_yaw_pca"): "(rotated_pc)",
+        (box, "_estimate_yaw_convex_hull"): "(rotated_pc)",
+        (box, "save_3d_with_ground_alignment_bbox"): "(scene_dir, bbox_method='pca')",
+        (cam, "length"): "(x, eps=1e-20)",
+        (cam, "safe_normalize"): "(x, eps=1e-20)",
+        (cam, "look_at"): "(campos, target, opengl=True)",
+        (cam, "orbit_camera"): "(elevation, azimuth, radius=1, is_degree=True, target=None, opengl=True)",
+    }
+    for (mod, name), sig in want.items():
+        assert str(inspect.signature(getattr(mod, name))) == sig, name
+    # estimate_bbox keeps the reference's four leading parameters and defaults; extras are keyword additions
+    params = list(inspect.signature(box.estimate_bbox).parameters.values())
+    assert [p.name for p in params[:4]] == ["in_pc", "cat_name", "ground_equ", "method"]
+    assert [p.default for p in params[1:4]] == [None, None, "pca"]
