@@ -2,23 +2,27 @@
 // (src/util.py:52-75 of the reference).  HBM-bound: 4 B read + 12 B (float) or
 // 24 B (double) written per pixel.
 //
-// One CTA owns a tile of kTilePx consecutive pixels of ONE image, so the camera
-// (inverse intrinsics, optional rigid transform) is prepared once per CTA in
-// shared memory.  Each thread handles 4 consecutive pixels per step and issues
-// all kUnroll 16-byte depth loads of its steps before the first use.
+// lift_prep_kernel + lift_tile_kernel (the fast path): the cameras of all images
+// (inverse intrinsics, optional rigid transform) are prepared once per launch by one
+// thread per image into a stream-ordered scratch buffer; the tile kernel then needs
+// no shared memory and no barrier: one CTA = 4096 consecutive pixels of one image,
+// each thread issues four 16-byte depth loads, reads its image's camera (uniform
+// loads) and writes 4 x 48 bytes.  One integer division per thread; the other pixel
+// coordinates advance incrementally.
+//
+// lift_scalar_kernel (generic fallback: pixel counts not divisible by 4, unaligned
+// buffers, no stream-ordered allocator): one pixel per thread, camera per CTA.
 #include "common.cuh"
 
 namespace la3d {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kUnroll = 4;
-constexpr int kStepPx = kThreads * 4;          // pixels per CTA step
-constexpr int kTilePx = kStepPx * kUnroll;     // pixels per CTA
+constexpr int kStepPx = kThreads * 4;   // pixels per CTA step
 
 struct Camera {
   double Kinv[9];   // exact path
-  double M[9];      // fast path: R @ Kinv
+  double M[9];      // fused path: R @ Kinv
   double t[3];
   double R[9];
 };
@@ -30,130 +34,184 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
                : "l"(p));
   return r;
 }
-__device__ __forceinline__ void st_stream(float4* p, float4 v) {
-  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+__device__ __forceinline__ void st_stream(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ void st_stream(double2* p, double2 v) {
-  asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+__device__ __forceinline__ void st_stream(double* p, double a, double b) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
-// kF64: the output dtype.  double -> reference operation order, bit for bit.
-// float -> one fused pass in double (ray = M.[u,v,1]; p = d*ray + t), rounded
-// once to float; pixels whose depth is not finite take the exact path so that
-// inf/NaN propagate exactly as in NumPy.
-template <bool kF64, bool kVec>
-__global__ void __launch_bounds__(kThreads) lift_kernel(const float* __restrict__ depth,
-                                                        const double* __restrict__ K, int k_stride,
-                                                        int k_is_inverse, const double* __restrict__ R,
-                                                        const double* __restrict__ t, int HW, int W,
-                                                        int tiles_per_image, void* __restrict__ out_) {
-  __shared__ Camera cam;
+__device__ __forceinline__ void prepare_camera(Camera& cam, const double* Kb, int k_is_inverse, const double* R,
+                                               const double* t) {
+  if (k_is_inverse) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) cam.Kinv[i] = Kb[i];
+  } else {
+    invert3x3(Kb, cam.Kinv);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) cam.t[i] = t ? t[i] : 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      cam.R[i * 3 + j] = R ? R[i * 3 + j] : (i == j ? 1.0 : 0.0);
+      cam.M[i * 3 + j] = R ? (R[i * 3 + 0] * cam.Kinv[0 * 3 + j] + R[i * 3 + 1] * cam.Kinv[1 * 3 + j] +
+                              R[i * 3 + 2] * cam.Kinv[2 * 3 + j])
+                           : cam.Kinv[i * 3 + j];
+    }
+}
+
+// One pixel, float32 result: a single fused float64 pass (ray = M.[u,v,1]; p = d*ray + t)
+// rounded once.  A non-finite depth takes the reference's exact operation order instead so
+// that inf / NaN propagate exactly as in NumPy.
+__device__ __forceinline__ void pixel_f32(float d, double ud, double vd, double r0, double r1, double r2,
+                                          const Camera& cam, const Camera* __restrict__ full, const double* Rp,
+                                          const double* tp, float& x, float& y, float& z) {
+  const double dd = (double)d;
+  if (isfinite(d)) {
+    x = (float)fma(dd, fma(cam.M[0], ud, r0), cam.t[0]);
+    y = (float)fma(dd, fma(cam.M[3], ud, r1), cam.t[1]);
+    z = (float)fma(dd, fma(cam.M[6], ud, r2), cam.t[2]);
+  } else {
+    double X, Y, Z;
+    lift_pixel_exact(dd, ud, vd, full->Kinv, X, Y, Z);
+    rigid_exact(Rp, tp, X, Y, Z);
+    x = (float)X; y = (float)Y; z = (float)Z;
+  }
+}
+
+// 4 consecutive pixels starting at (v,u) of one image -> 48 bytes
+__device__ __forceinline__ void quad_f32(const float4 dq, int u, int v, int W, const Camera& cam,
+                                         const Camera* __restrict__ full, const double* Rp, const double* tp,
+                                         float* __restrict__ dst) {
+  float x0, y0, z0, x1, y1, z1, x2, y2, z2, x3, y3, z3;
+  const double vd = (double)v, ud = (double)u;
+  const double r0 = fma(cam.M[1], vd, cam.M[2]), r1 = fma(cam.M[4], vd, cam.M[5]), r2 = fma(cam.M[7], vd, cam.M[8]);
+  if (u + 3 < W) {
+    pixel_f32(dq.x, ud, vd, r0, r1, r2, cam, full, Rp, tp, x0, y0, z0);
+    pixel_f32(dq.y, ud + 1.0, vd, r0, r1, r2, cam, full, Rp, tp, x1, y1, z1);
+    pixel_f32(dq.z, ud + 2.0, vd, r0, r1, r2, cam, full, Rp, tp, x2, y2, z2);
+    pixel_f32(dq.w, ud + 3.0, vd, r0, r1, r2, cam, full, Rp, tp, x3, y3, z3);
+  } else {   // the quad wraps to the next row (W not a multiple of 4)
+    int uu = u, vv = v;
+    auto one = [&](float d, float& x, float& y, float& z) {
+      const double vq = (double)vv;
+      pixel_f32(d, (double)uu, vq, fma(cam.M[1], vq, cam.M[2]), fma(cam.M[4], vq, cam.M[5]),
+                fma(cam.M[7], vq, cam.M[8]), cam, full, Rp, tp, x, y, z);
+      if (++uu == W) { uu = 0; ++vv; }
+    };
+    one(dq.x, x0, y0, z0); one(dq.y, x1, y1, z1); one(dq.z, x2, y2, z2); one(dq.w, x3, y3, z3);
+  }
+  st_stream(dst, x0, y0, z0, x1);
+  st_stream(dst + 4, y1, z1, x2, y2);
+  st_stream(dst + 8, z2, x3, y3, z3);
+}
+
+// float64 result: the reference's operation order, bit for bit
+__device__ __forceinline__ void quad_f64(const float4 dq, int u, int v, int W, const Camera& cam, const double* Rp,
+                                         const double* tp, double* __restrict__ dst) {
+  double x0, y0, z0, x1, y1, z1;
+  int uu = u, vv = v;
+  auto one = [&](float d, double& x, double& y, double& z) {
+    lift_pixel_exact((double)d, (double)uu, (double)vv, cam.Kinv, x, y, z);
+    rigid_exact(Rp, tp, x, y, z);
+    if (++uu == W) { uu = 0; ++vv; }
+  };
+  one(dq.x, x0, y0, z0); one(dq.y, x1, y1, z1);
+  st_stream(dst, x0, y0); st_stream(dst + 2, z0, x1); st_stream(dst + 4, y1, z1);
+  one(dq.z, x0, y0, z0); one(dq.w, x1, y1, z1);
+  st_stream(dst + 6, x0, y0); st_stream(dst + 8, z0, x1); st_stream(dst + 10, y1, z1);
+}
+
+// Cameras of all images, prepared once per launch by lift_prep_kernel.
+__global__ void lift_prep_kernel(const double* __restrict__ K, int k_stride, int k_is_inverse,
+                                 const double* __restrict__ R, const double* __restrict__ t, int B,
+                                 Camera* __restrict__ cams) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) prepare_camera(cams[b], K + (size_t)b * k_stride, k_is_inverse, R, t);
+}
+
+// One CTA = kQuads x 1024 consecutive pixels of ONE image.  No shared memory, no barrier:
+// every thread issues its kQuads 16-byte depth loads, then reads its image's camera
+// (uniform, L1/L2-resident) and converts quad by quad.
+template <bool kF64, int kQuads, int kMinCtas>
+__global__ void __launch_bounds__(kThreads, kMinCtas)
+    lift_tile_kernel(const float* __restrict__ depth, const Camera* __restrict__ cams, int has_R, int has_t, int HW,
+                     int W, int tiles_per_image, void* __restrict__ out_) {
   const int b = blockIdx.x / tiles_per_image;
   const int tile = blockIdx.x - b * tiles_per_image;
-  const int tile_px = tile * kTilePx;
+  int px = tile * (kQuads * kStepPx) + threadIdx.x * 4;
   const float* img = depth + (size_t)b * HW;
-
-  // Issue this thread's depth loads first; the camera set-up below overlaps them.
-  float4 dv[kUnroll];
-  if (kVec) {
+  float4 dq[kQuads];
 #pragma unroll
-    for (int j = 0; j < kUnroll; ++j) {
-      int px = tile_px + j * kStepPx + threadIdx.x * 4;
-      dv[j] = (px < HW) ? ld_stream(reinterpret_cast<const float4*>(img + px)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  for (int q = 0; q < kQuads; ++q)
+    dq[q] = (px + q * kStepPx < HW) ? ld_stream(reinterpret_cast<const float4*>(img + px + q * kStepPx))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+  const Camera* gc = cams + b;
+  Camera cam;                       // only the fields a path touches are actually loaded
+  if (kF64) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) cam.Kinv[i] = __ldg(&gc->Kinv[i]);
   } else {
 #pragma unroll
-    for (int j = 0; j < kUnroll; ++j) {
-      int px = tile_px + j * kStepPx + threadIdx.x * 4;
-      float e[4];
+    for (int i = 0; i < 9; ++i) cam.M[i] = __ldg(&gc->M[i]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) e[q] = (px + q < HW) ? __ldg(img + px + q) : 0.f;
-      dv[j] = make_float4(e[0], e[1], e[2], e[3]);
-    }
+    for (int i = 0; i < 3; ++i) cam.t[i] = __ldg(&gc->t[i]);
   }
+  const double* Rp = has_R ? gc->R : nullptr;
+  const double* tp = has_t ? gc->t : nullptr;
+  int v = px / W, u = px - v * W;
+  const int dv = kStepPx / W, du = kStepPx - dv * W;
+#pragma unroll
+  for (int q = 0; q < kQuads; ++q) {
+    if (px < HW) {
+      const size_t o = ((size_t)b * HW + px) * 3;
+      if (kF64) quad_f64(dq[q], u, v, W, cam, Rp, tp, reinterpret_cast<double*>(out_) + o);
+      else quad_f32(dq[q], u, v, W, cam, gc, Rp, tp, reinterpret_cast<float*>(out_) + o);
+    }
+    px += kStepPx;
+    u += du; v += dv;
+    if (u >= W) { u -= W; ++v; }
+  }
+}
 
-  if (threadIdx.x == 0) {
-    const double* Kb = K + (size_t)b * k_stride;
-    if (k_is_inverse) {
-#pragma unroll
-      for (int i = 0; i < 9; ++i) cam.Kinv[i] = Kb[i];
-    } else {
-      invert3x3(Kb, cam.Kinv);
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) cam.t[i] = t ? t[i] : 0.0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        cam.R[i * 3 + j] = R ? R[i * 3 + j] : (i == j ? 1.0 : 0.0);
-        cam.M[i * 3 + j] = R ? (R[i * 3 + 0] * cam.Kinv[0 * 3 + j] + R[i * 3 + 1] * cam.Kinv[1 * 3 + j] +
-                                R[i * 3 + 2] * cam.Kinv[2 * 3 + j])
-                             : cam.Kinv[i * 3 + j];
-      }
-  }
+// Generic fallback: one pixel per thread; blockIdx.y = image.
+template <bool kF64>
+__global__ void __launch_bounds__(kThreads) lift_scalar_kernel(const float* __restrict__ depth,
+                                                               const double* __restrict__ K, int k_stride,
+                                                               int k_is_inverse, const double* __restrict__ R,
+                                                               const double* __restrict__ t, int HW, int W,
+                                                               void* __restrict__ out_) {
+  __shared__ Camera cam;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) prepare_camera(cam, K + (size_t)b * k_stride, k_is_inverse, R, t);
   __syncthreads();
   const double* Rp = R ? cam.R : nullptr;
   const double* tp = t ? cam.t : nullptr;
-
-#pragma unroll
-  for (int j = 0; j < kUnroll; ++j) {
-    const int px = tile_px + j * kStepPx + threadIdx.x * 4;
-    if (px >= HW) continue;
-    int v = px / W;
-    int u = px - v * W;
-    const float dd[4] = {dv[j].x, dv[j].y, dv[j].z, dv[j].w};
-    double o[12];
+  for (int p = blockIdx.x * kThreads + threadIdx.x; p < HW; p += gridDim.x * kThreads) {
+    const int v = p / W, u = p - v * W;
+    const float d = __ldg(depth + (size_t)b * HW + p);
+    const size_t o = ((size_t)b * HW + p) * 3;
     if (kF64) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        lift_pixel_exact((double)dd[q], (double)u, (double)v, cam.Kinv, o[q * 3], o[q * 3 + 1], o[q * 3 + 2]);
-        rigid_exact(Rp, tp, o[q * 3], o[q * 3 + 1], o[q * 3 + 2]);
-        if (++u == W) { u = 0; ++v; }
-      }
+      double x, y, z;
+      lift_pixel_exact((double)d, (double)u, (double)v, cam.Kinv, x, y, z);
+      rigid_exact(Rp, tp, x, y, z);
+      double* dst = reinterpret_cast<double*>(out_) + o;
+      dst[0] = x; dst[1] = y; dst[2] = z;
     } else {
-      double vd = (double)v, ud = (double)u;
-      double r0 = fma(cam.M[1], vd, cam.M[2]), r1 = fma(cam.M[4], vd, cam.M[5]), r2 = fma(cam.M[7], vd, cam.M[8]);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        double d = (double)dd[q];
-        if (isfinite(dd[q])) {
-          o[q * 3 + 0] = fma(d, fma(cam.M[0], ud, r0), cam.t[0]);
-          o[q * 3 + 1] = fma(d, fma(cam.M[3], ud, r1), cam.t[1]);
-          o[q * 3 + 2] = fma(d, fma(cam.M[6], ud, r2), cam.t[2]);
-        } else {
-          lift_pixel_exact(d, ud, vd, cam.Kinv, o[q * 3], o[q * 3 + 1], o[q * 3 + 2]);
-          rigid_exact(Rp, tp, o[q * 3], o[q * 3 + 1], o[q * 3 + 2]);
-        }
-        ud += 1.0;
-        if (++u == W) {
-          u = 0; ud = 0.0; ++v; vd += 1.0;
-          r0 = fma(cam.M[1], vd, cam.M[2]); r1 = fma(cam.M[4], vd, cam.M[5]); r2 = fma(cam.M[7], vd, cam.M[8]);
-        }
-      }
-    }
-    const int n = min(4, HW - px);
-    if (kF64) {
-      double* dst = reinterpret_cast<double*>(out_) + ((size_t)b * HW + px) * 3;
-      if (kVec) {
-#pragma unroll
-        for (int q = 0; q < 6; ++q) st_stream(reinterpret_cast<double2*>(dst) + q, make_double2(o[2 * q], o[2 * q + 1]));
-      } else {
-        for (int q = 0; q < 3 * n; ++q) dst[q] = o[q];
-      }
-    } else {
-      float* dst = reinterpret_cast<float*>(out_) + ((size_t)b * HW + px) * 3;
-      if (kVec) {
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-          st_stream(reinterpret_cast<float4*>(dst) + q,
-                    make_float4((float)o[4 * q], (float)o[4 * q + 1], (float)o[4 * q + 2], (float)o[4 * q + 3]));
-      } else {
-        for (int q = 0; q < 3 * n; ++q) dst[q] = (float)o[q];
-      }
+      const double vd = (double)v;
+      float x, y, z;
+      pixel_f32(d, (double)u, vd, fma(cam.M[1], vd, cam.M[2]), fma(cam.M[4], vd, cam.M[5]),
+                fma(cam.M[7], vd, cam.M[8]), cam, &cam, Rp, tp, x, y, z);
+      float* dst = reinterpret_cast<float*>(out_) + o;
+      dst[0] = x; dst[1] = y; dst[2] = z;
     }
   }
 }
+
+constexpr int kQuads = 4;      // 16-byte loads in flight per thread
+constexpr int kMinCtas = 3;    // resident CTAs per SM the tile kernels are compiled for
 
 }  // namespace
 }  // namespace la3d
@@ -166,16 +224,31 @@ extern "C" int la3d_depth_lift(const float* depth, const double* K, int k_stride
   LA3D_REQUIRE(k_stride == 0 || k_stride == 9, "k_stride must be 0 (shared) or 9 (per image)");
   LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
   const int HW = H * W;
-  const int tiles = (HW + kTilePx - 1) / kTilePx;
-  LA3D_REQUIRE((long long)tiles * B < (1ll << 31), "grid too large");
-  const bool vec = (HW % 4 == 0) && aligned16(depth) && aligned16(out);
-  dim3 grid((unsigned)(tiles * B)), block(kThreads);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define LAUNCH(F64, VEC) \
-  lift_kernel<F64, VEC><<<grid, block, 0, s>>>(depth, K, k_stride, k_is_inverse, R, t, HW, W, tiles, out)
-  if (out_f64) { if (vec) LAUNCH(true, true); else LAUNCH(true, false); }
-  else         { if (vec) LAUNCH(false, true); else LAUNCH(false, false); }
-#undef LAUNCH
+  const bool vec = (HW % 4 == 0) && aligned16(depth) && aligned16(out);
+  Camera* cams = nullptr;
+  if (vec && cudaMallocAsync(reinterpret_cast<void**>(&cams), sizeof(Camera) * (size_t)B, s) != cudaSuccess) {
+    cudaGetLastError();   // no stream-ordered pool on this driver: use the self-contained fallback below
+    cams = nullptr;
+  }
+  if (cams) {
+    // cameras once per launch (B threads), then one CTA per 4096-pixel tile of one image
+    lift_prep_kernel<<<(B + 127) / 128, 128, 0, s>>>(K, k_stride, k_is_inverse, R, t, B, cams);
+    const int tiles = (HW + kQuads * kStepPx - 1) / (kQuads * kStepPx);
+    LA3D_REQUIRE((long long)tiles * B < (1ll << 31), "grid too large");
+    const unsigned grid = (unsigned)(tiles * B);
+    if (out_f64)
+      lift_tile_kernel<true, kQuads, kMinCtas><<<grid, kThreads, 0, s>>>(depth, cams, R != nullptr, t != nullptr, HW, W, tiles, out);
+    else
+      lift_tile_kernel<false, kQuads, kMinCtas><<<grid, kThreads, 0, s>>>(depth, cams, R != nullptr, t != nullptr, HW, W, tiles, out);
+    LA3D_CUDA(cudaGetLastError());
+    LA3D_CUDA(cudaFreeAsync(cams, s));
+  } else {
+    LA3D_REQUIRE(B <= 65535, "fallback path supports at most 65535 images per call");
+    dim3 grid((unsigned)min((HW + kThreads - 1) / kThreads, 4096), (unsigned)B);
+    if (out_f64) lift_scalar_kernel<true><<<grid, kThreads, 0, s>>>(depth, K, k_stride, k_is_inverse, R, t, HW, W, out);
+    else lift_scalar_kernel<false><<<grid, kThreads, 0, s>>>(depth, K, k_stride, k_is_inverse, R, t, HW, W, out);
+  }
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
 }

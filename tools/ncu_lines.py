@@ -27,7 +27,12 @@ rows = list(csv.reader(out.splitlines()))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 idx = {h: i for i, h in enumerate(hdr)}
-sass = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+sass = []
+for r in rows[hi + 1:]:
+    if r and r[0] == "Address":
+        break                      # ncu prints the listing twice
+    if len(r) == len(hdr):
+        sass.append(r)
 print(rows[0][1] if rows and len(rows[0]) > 1 else "", f"-- {len(sass)} SASS instructions")
 
 tmp = tempfile.mkdtemp()
@@ -37,10 +42,12 @@ for cub in glob.glob(os.path.join(tmp, "*.cubin")):
     if os.path.basename(cub).count("-") > 1:
         continue
     dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout.splitlines()
-    inside, cur = False, ("?", 0)
+    inside, cur, done = False, ("?", 0), False
     for ln in dis:
         if ln.startswith("//---") and ".text." in ln:
-            inside = mangled in ln
+            if inside:
+                done = True        # first matching function only
+            inside = (mangled in ln) and not done
             continue
         if not inside:
             continue
