@@ -92,17 +92,18 @@ int la3d_depth_lift(const float* depth, const double* K, int k_stride, int k_is_
  * Mask-stack scan.  Replaces the NumPy boolean-gather bookkeeping of pts[mask]
  * (src/util.py:480-481 idiom; mask stack of src/util.py:382): one pass over the
  * [B][I][H][W] byte masks produces, per plane, a bit mask (bit k of word w is
- * pixel 32*w+k) and the number of set pixels in every 512-pixel chunk, which
+ * pixel 32*w+k) and, for every 512-pixel chunk, the number of set pixels of its four
+ * 128-pixel quarters packed as four bytes (byte q = quarter q, each 0..128), which
  * together locate the r-th set pixel in row-major order (= row r of pts[mask]).
  *   masks         [B*I][H*W] uint8; nonzero = set (mask_is_01 = 1 promises 0/1 bytes,
  *                 which is what numpy/torch bool arrays hold, and takes a shorter path)
  *   bits          [B*I][la3d_words_per_plane(H,W)] uint32
- *   chunk_counts  [B*I][la3d_chunks_per_plane(H,W)] uint16
+ *   chunk_counts  [B*I][la3d_chunks_per_plane(H,W)] uint32 (4 x uint8 quarter counts)
  * ------------------------------------------------------------------------- */
 size_t la3d_chunks_per_plane(int H, int W);
 size_t la3d_words_per_plane(int H, int W);
 int la3d_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
-                   uint16_t* chunk_counts, la3d_stream_t stream);
+                   uint32_t* chunk_counts, la3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Per-image subsample ranks.  Replaces `np.random.randint(0, N, 500)` of
@@ -113,7 +114,7 @@ int la3d_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_0
  *   counts [B*I] int32  (out) set pixels per plane
  *   ranks  [B*I][500] int32 (out) row indices into pts[mask]; untouched when N <= 500
  * ------------------------------------------------------------------------- */
-int la3d_sample_ranks(const uint16_t* chunk_counts, int B, int I, int H, int W, uint32_t seed, uint32_t image_offset,
+int la3d_sample_ranks(const uint32_t* chunk_counts, int B, int I, int H, int W, uint32_t seed, uint32_t image_offset,
                       int32_t* counts, int32_t* ranks, la3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
@@ -126,7 +127,7 @@ int la3d_sample_ranks(const uint16_t* chunk_counts, int B, int I, int H, int W, 
  *   records [B*I][64] float (rec_f64 = 0) or double (rec_f64 = 1)
  * ------------------------------------------------------------------------- */
 int la3d_fit_scanned(const float* depth, const double* K, const double* ground, const uint32_t* bits,
-                     const uint16_t* chunk_counts, const int32_t* counts, const int32_t* ranks, int B, int I, int H,
+                     const uint32_t* chunk_counts, const int32_t* counts, const int32_t* ranks, int B, int I, int H,
                      int W, int method, int yaw_steps, void* records, int rec_f64, la3d_stream_t stream);
 
 /* The three calls above back to back.  `workspace` needs la3d_fit_workspace_bytes(). */

@@ -24,7 +24,7 @@ int cuda_fail(cudaError_t err, const char* what) {
 
 struct Workspace {
   uint32_t* bits;
-  uint16_t* chunk_counts;
+  uint32_t* chunk_counts;
   int32_t* counts;
   int32_t* ranks;
   size_t bytes;
@@ -39,7 +39,7 @@ static Workspace carve(void* base, int B, int I, int H, int W) {
   Workspace w{};
   size_t off = 0;
   w.bits = reinterpret_cast<uint32_t*>(p + off);          off = up(off + planes * words * 4);
-  w.chunk_counts = reinterpret_cast<uint16_t*>(p + off);  off = up(off + planes * chunks * 2);
+  w.chunk_counts = reinterpret_cast<uint32_t*>(p + off);  off = up(off + planes * chunks * 4);
   w.counts = reinterpret_cast<int32_t*>(p + off);         off = up(off + planes * 4);
   w.ranks = reinterpret_cast<int32_t*>(p + off);          off = up(off + planes * LA3D_SUBSAMPLE * 4);
   w.bytes = off;

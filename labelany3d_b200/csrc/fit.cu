@@ -2,15 +2,20 @@
 // estimators (src/util_3dbox.py:106-224 of the reference) and the corner
 // reprojection (src/util.py:227-229, src/tools/combine_results.py:238-246).
 //
-// One CTA of 128 threads fits one box from at most 500 points, all in float64:
+// One CTA of 64 threads fits one box from at most 500 points, all in float64:
 //   1. point source
-//      - scanned masks: rank r (the reference's random row of pts[mask]) ->
-//        binary search over the per-chunk prefix sums -> bit select in the
-//        chunk's 16 words -> pixel (v,u) -> depth gather -> exact lift
-//        (src/util.py:72 operation order);
+//      - scanned masks: rank r (the reference's random row of pts[mask]) -> binary
+//        search over the per-chunk prefix sums -> quarter of the chunk (packed byte
+//        counts) -> bit select in that quarter's 4 words -> pixel (v,u) -> depth gather
+//        -> exact lift (src/util.py:72 operation order); the eight samples of a thread
+//        move through that chain together, so a box pays four global round trips;
 //      - explicit points (the reference's own call pattern, util_3dbox.py:269-278).
 //   2. ground alignment p @ Rg, NaN-row filter (util_3dbox.py:128-143);
-//   3. yaw: PCA closed form | convex-hull edge search | uniform sweep;
+//   3. yaw: PCA closed form | convex-hull edge search | uniform sweep.  Hull and sweep
+//      first discard every point strictly inside the octagon of the footprint's 8
+//      extreme points (such a point is never extreme in any direction); the sweep
+//      then evaluates its candidates over the survivors, the hull method gift-wraps
+//      them (one warp) and visits the hull edges;
 //   4. extents at that yaw, float16-rounded corners, back-rotation with the
 //      reference's Rg / Rg^T convention, centre, dimensions, R_cam (:154-176);
 //   5. projection of the 8 corners and their 2D bounds.
@@ -22,16 +27,17 @@
 namespace la3d {
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 64;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxPts = 512;   // >= LA3D_SUBSAMPLE
+constexpr int kGroup = 8;      // samples per thread = ceil(500 / 64): all in flight together
 constexpr unsigned kFull = 0xffffffffu;
 
 struct FitArgs {
   // scanned-mask source
   const float* depth;
   const uint32_t* bits;
-  const uint16_t* chunk_counts;
+  const uint32_t* chunk_counts;
   const int32_t* counts;
   const int32_t* ranks;
   int I, HW, W, chunks;
@@ -47,14 +53,31 @@ struct FitArgs {
   int rec_f64;
 };
 
+// Static shared memory.  The y coordinate is not kept: only its minimum / maximum matter (they do
+// not depend on the yaw) and those are reduced on the fly.
 struct Smem {
-  double x[kMaxPts], y[kMaxPts], z[kMaxPts];   // ground-aligned points; x = NaN marks a dropped row
-  double hx[kMaxPts], hz[kMaxPts];             // hull vertices, counter-clockwise
+  double x[kMaxPts], z[kMaxPts];               // ground-aligned footprint; x = NaN marks a dropped row
   double red[kWarps][8];
   double Kinv[9], Kmat[9], Rg[9];
-  double rec[LA3D_REC];
+  double oct[8][2];                            // extreme points of the footprint (octagon, CCW)
+  double yaw, cos_yaw, sin_yaw;
   int ired[kWarps][4];
+  int cand_n, hull_n;
+  double* rec;                                 // [64] record under construction (aliases the prefix table)
+  unsigned short* cand;                        // points that can be extreme in some direction
+  unsigned short* hull;                        // hull vertices (indices into x/z), counter-clockwise
 };
+
+// Dynamic shared memory: [areas: n_areas doubles][prefix table (chunks+1 u32) / record (64 doubles)]
+//                        [cand: 512 u16 (hull, sweep)][hull: 512 u16 (hull)]
+__host__ __device__ inline size_t region_b_bytes(int chunks, bool scanned) {
+  size_t pref = scanned ? ((size_t)chunks + 1) * 4 : 0;
+  size_t need = pref > (size_t)LA3D_REC * 8 ? pref : (size_t)LA3D_REC * 8;
+  return (need + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }   // NaN in b is ignored
+__device__ __forceinline__ double dmax(double a, double b) { return b > a ? b : a; }
 
 // ---- block-wide reductions; the result is broadcast to every thread -------------
 template <int N, typename Op>
@@ -63,7 +86,7 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], Smem& sm, Op op) {
 #pragma unroll
   for (int k = 0; k < N; ++k)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[k] = op(v[k], __shfl_xor_sync(kFull, v[k], o));
+    for (int o = 16; o > 0; o >>= 1) v[k] = op(v[k], __shfl_xor_sync(kFull, v[k], o), k);
   __syncthreads();
   if (lane == 0)
 #pragma unroll
@@ -73,7 +96,7 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], Smem& sm, Op op) {
   for (int k = 0; k < N; ++k) {
     double acc = sm.red[0][k];
 #pragma unroll
-    for (int w = 1; w < kWarps; ++w) acc = op(acc, sm.red[w][k]);
+    for (int w = 1; w < kWarps; ++w) acc = op(acc, sm.red[w][k], k);
     v[k] = acc;
   }
 }
@@ -97,9 +120,11 @@ __device__ __forceinline__ void block_sum_int(int (&v)[N], Smem& sm) {
   }
 }
 
-struct OpAdd { __device__ double operator()(double a, double b) const { return a + b; } };
-struct OpMin { __device__ double operator()(double a, double b) const { return fmin(a, b); } };
-struct OpMax { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
+struct OpAdd { __device__ double operator()(double a, double b, int) const { return a + b; } };
+// entries 0..2 are minima, 3..5 maxima
+struct OpMinMax { __device__ double operator()(double a, double b, int k) const { return k < 3 ? dmin(a, b) : dmax(a, b); } };
+// entries 0..3 are maxima, 4..7 minima
+struct OpMax4Min4 { __device__ double operator()(double a, double b, int k) const { return k < 4 ? dmax(a, b) : dmin(a, b); } };
 
 // (area, index) pairs ordered like the reference's `if area < min_area` loop: the
 // smallest area wins, the earliest index among equals; NaN and +inf never win.
@@ -107,7 +132,7 @@ struct Best {
   double area;
   int idx;   // -1 = nothing qualified yet
   __device__ void offer(double a, int i) {
-    if (!(a < CUDART_INF)) return;
+    if (!(a < CUDART_INF) || i < 0) return;
     if (idx < 0 || a < area || (a == area && i < idx)) { area = a; idx = i; }
   }
 };
@@ -120,15 +145,14 @@ __device__ __forceinline__ int first_strict_min(const double* areas, int n, Smem
   for (int o = 16; o > 0; o >>= 1) {
     const double oa = __shfl_xor_sync(kFull, b.area, o);
     const int oi = __shfl_xor_sync(kFull, b.idx, o);
-    if (oi >= 0) b.offer(oa, oi);
+    b.offer(oa, oi);
   }
   __syncthreads();
   if (lane == 0) { sm.red[warp][0] = b.area; sm.ired[warp][0] = b.idx; }
   __syncthreads();
   Best r{CUDART_INF, -1};
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w)
-    if (sm.ired[w][0] >= 0) r.offer(sm.red[w][0], sm.ired[w][0]);
+  for (int w = 0; w < kWarps; ++w) r.offer(sm.red[w][0], sm.ired[w][0]);
   return r.idx;
 }
 
@@ -162,188 +186,214 @@ __device__ void ground_rotation(const double* g, double* Rg) {
     }
 }
 
-// r-th (0-based) set pixel of a plane in row-major order.  pref = exclusive prefix
-// sums of the chunk counts, pref[chunks] = N.
-__device__ __forceinline__ int select_pixel(const uint32_t* __restrict__ plane_bits, const uint32_t* pref, int chunks,
-                                            uint32_t r) {
-  int lo = 0, hi = chunks;            // invariant: pref[lo] <= r < pref[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (pref[mid] <= r) lo = mid; else hi = mid;
-  }
-  uint32_t rem = r - pref[lo];
-  const uint4* w4 = reinterpret_cast<const uint4*>(plane_bits + (size_t)lo * kChunkWords);
-  uint32_t w[kChunkWords];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint4 t = __ldg(w4 + q);
-    w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
-  }
-  int word = 0;
-  uint32_t sel = w[0];
-#pragma unroll
-  for (int q = 0; q < kChunkWords - 1; ++q) {
-    const uint32_t pc = __popc(w[q]);
-    if (word == q && rem >= pc) { rem -= pc; word = q + 1; sel = w[q + 1]; }
-  }
-  return lo * kChunkPx + word * 32 + (int)__fns(sel, 0, (int)rem + 1);
-}
-
 // ---- yaw estimators -----------------------------------------------------------------
 
 // util_3dbox.py:181-186 with scikit-learn's arithmetic in closed form:
 // C = (X^T X - n mu mu^T)/(n-1); first eigenvector angle theta = atan2(2b, a-c)/2; the
 // component of larger magnitude is made positive (svd_flip, v-based).
-__device__ double yaw_pca(Smem& sm, int nsel, int n_valid) {
+__device__ void yaw_pca(Smem& sm, int nsel, int n_valid) {
   double s[5] = {0, 0, 0, 0, 0};
   for (int k = threadIdx.x; k < nsel; k += kThreads) {
     const double px = sm.x[k], pz = sm.z[k];
     if (px == px) { s[0] += px; s[1] += pz; s[2] += px * px; s[3] += px * pz; s[4] += pz * pz; }
   }
   block_reduce(s, sm, OpAdd());
-  const double n = (double)n_valid;
-  const double mx = s[0] / n, mz = s[1] / n;
-  const double ca = (s[2] - n * mx * mx) / (n - 1.0);
-  const double cb = (s[3] - n * mx * mz) / (n - 1.0);
-  const double cc = (s[4] - n * mz * mz) / (n - 1.0);
-  const double theta = 0.5 * atan2(2.0 * cb, ca - cc);
-  double vz, vx;
-  sincos(theta, &vz, &vx);
-  if (fabs(vx) >= fabs(vz)) { if (vx < 0.0) { vx = -vx; vz = -vz; } }
-  else if (vz < 0.0) { vx = -vx; vz = -vz; }
-  return atan2(vz, vx);
+  if (threadIdx.x == 0) {
+    const double n = (double)n_valid;
+    const double mx = s[0] / n, mz = s[1] / n;
+    const double ca = (s[2] - n * mx * mx) / (n - 1.0);
+    const double cb = (s[3] - n * mx * mz) / (n - 1.0);
+    const double cc = (s[4] - n * mz * mz) / (n - 1.0);
+    const double theta = 0.5 * atan2(2.0 * cb, ca - cc);
+    double vz, vx;
+    sincos(theta, &vz, &vx);
+    if (fabs(vx) >= fabs(vz)) { if (vx < 0.0) { vx = -vx; vz = -vz; } }
+    else if (vz < 0.0) { vx = -vx; vz = -vz; }
+    // yaw = atan2(vz, vx) (:186); (vx, vz) already is (cos yaw, sin yaw), which is all the
+    // extents need - the angle itself is only reported
+    sm.cos_yaw = vx; sm.sin_yaw = vz;
+    sm.yaw = atan2(vz, vx);
+  }
 }
 
-// New feature: yaw_k = k*(pi/2)/K, area of the XZ bounding
-// rectangle after yaw_matrix(yaw_k), first strict minimum.  One warp per candidate.
-__device__ double yaw_sweep(Smem& sm, int nsel, int K, double* areas, bool inf_y) {
-  if (inf_y || K <= 0) return 0.0;     // 0*inf = NaN in every area: nothing beats +inf
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = warp; c < K; c += kWarps) {
-    const double ang = __ddiv_rn(__dmul_rn((double)c, CUDART_PIO2), (double)K);
-    double s, co;
-    sincos(ang, &s, &co);
-    double mnx = CUDART_INF, mxx = -CUDART_INF, mnz = CUDART_INF, mxz = -CUDART_INF;
-    for (int k = lane; k < nsel; k += 32) {
-      const double px = sm.x[k], pz = sm.z[k];      // dropped rows carry NaN and fall out of fmin/fmax
-      const double rx = co * px + s * pz, rz = co * pz - s * px;
-      mnx = fmin(mnx, rx); mxx = fmax(mxx, rx); mnz = fmin(mnz, rz); mxz = fmax(mxz, rz);
-    }
+// Octagon filter.  The 8 points that maximise x, x+z, z, z-x, -x, -x-z, -z, x-z (in that,
+// counter-clockwise, order of direction) span a convex polygon of input points; a point
+// strictly inside it can never attain the maximum of a linear functional over the cloud, so
+// rectangle extents (sweep, hull-edge search) and the hull itself only need the others.
+// Degenerate edges (repeated extreme points) are skipped, which only keeps more points.
+__device__ void octagon_candidates(Smem& sm, int nsel) {
+  const int lane = threadIdx.x & 31;
+  double e[8] = {-CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF, CUDART_INF, CUDART_INF, CUDART_INF, CUDART_INF};
+  for (int k = threadIdx.x; k < nsel; k += kThreads) {
+    const double px = sm.x[k], pz = sm.z[k];       // dropped rows are NaN and lose every comparison
+    e[0] = dmax(e[0], px); e[1] = dmax(e[1], px + pz); e[2] = dmax(e[2], pz); e[3] = dmax(e[3], pz - px);
+    e[4] = dmin(e[4], px); e[5] = dmin(e[5], px + pz); e[6] = dmin(e[6], pz); e[7] = dmin(e[7], pz - px);
+  }
+  block_reduce(e, sm, OpMax4Min4());
+  if (threadIdx.x == 0) sm.cand_n = 0;
+  // any point attaining an extreme serves as that octagon vertex (ties write the same role; either is valid)
+  for (int k = threadIdx.x; k < nsel; k += kThreads) {
+    const double px = sm.x[k], pz = sm.z[k];
+    const double f[8] = {px, px + pz, pz, pz - px, px, px + pz, pz, pz - px};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mnx = fmin(mnx, __shfl_xor_sync(kFull, mnx, o));
-      mxx = fmax(mxx, __shfl_xor_sync(kFull, mxx, o));
-      mnz = fmin(mnz, __shfl_xor_sync(kFull, mnz, o));
-      mxz = fmax(mxz, __shfl_xor_sync(kFull, mxz, o));
-    }
-    if (lane == 0) areas[c] = (mxx - mnx) * (mxz - mnz);
+    for (int d = 0; d < 8; ++d)
+      if (f[d] == e[d]) { sm.oct[d][0] = px; sm.oct[d][1] = pz; }
   }
   __syncthreads();
-  const int best = first_strict_min(areas, K, sm);
-  return best < 0 ? 0.0 : __ddiv_rn(__dmul_rn((double)best, CUDART_PIO2), (double)K);
+  double ox[8], oz[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) { ox[d] = sm.oct[d][0]; oz[d] = sm.oct[d][1]; }
+  for (int k0 = 0; k0 < nsel; k0 += kThreads) {
+    const int k = k0 + threadIdx.x;
+    bool keep = false;
+    if (k < nsel) {
+      const double px = sm.x[k], pz = sm.z[k];
+      if (px == px) {
+        bool inside = true;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          const int n = (d + 1) & 7;
+          const double ex = ox[n] - ox[d], ez = oz[n] - oz[d];
+          if (ex != 0.0 || ez != 0.0) inside = inside && (ex * (pz - oz[d]) - ez * (px - ox[d]) > 0.0);
+        }
+        keep = !inside;
+      }
+    }
+    const unsigned bal = __ballot_sync(kFull, keep);
+    int base = 0;
+    if (lane == 0 && bal) base = atomicAdd(&sm.cand_n, __popc(bal));
+    base = __shfl_sync(kFull, base, 0);
+    if (keep) sm.cand[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)k;
+  }
+  __syncthreads();
 }
 
-// Gift wrapping of the valid XZ points, counter-clockwise from the lexicographically
-// smallest point; collinear points are skipped (strict hull, like Qhull's vertex list).
-// Returns the vertex count, or 0 when Qhull would have raised (< 3 vertices).
+// Gift wrapping of the valid XZ points by warp 0, counter-clockwise from the
+// lexicographically smallest point; collinear points are skipped (strict hull, like Qhull's
+// vertex list).  Writes sm.hull / sm.hull_n; hull_n = 0 when Qhull would have raised
+// (fewer than 3 vertices: coincident or collinear points).
 struct Wrap {
   double cx, cz, qx, qz;
-  __device__ bool none() const { return qx == cx && qz == cz; }
-  __device__ void offer(double px, double pz) {
-    if (!(px == px) || (px == cx && pz == cz)) return;
-    if (none()) { qx = px; qz = pz; return; }
+  int qi;
+  __device__ void offer(double px, double pz, int pi) {
+    if (pi < 0 || !(px == px) || (px == cx && pz == cz)) return;
+    if (qi < 0) { qx = px; qz = pz; qi = pi; return; }
     const double cr = (qx - cx) * (pz - cz) - (qz - cz) * (px - cx);
-    if (cr < 0.0) { qx = px; qz = pz; }          // p is clockwise of cur->q: q cannot be next
-    else if (cr == 0.0) {
+    bool take = cr < 0.0;                       // p is clockwise of cur->q: q cannot be the next vertex
+    if (cr == 0.0) {
       const double dq = (qx - cx) * (qx - cx) + (qz - cz) * (qz - cz);
       const double dp = (px - cx) * (px - cx) + (pz - cz) * (pz - cz);
-      if (dp > dq) { qx = px; qz = pz; }
+      take = dp > dq || (dp == dq && pi < qi);
     }
+    if (take) { qx = px; qz = pz; qi = pi; }
   }
 };
 
-__device__ int hull_wrap(Smem& sm, int nsel) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ void hull_wrap(Smem& sm) {
+  const int lane = threadIdx.x & 31;
+  const int nc = sm.cand_n;
+  // start vertex: lexicographic minimum (x, then z, then index)
   double bx = CUDART_INF, bz = CUDART_INF;
-  auto lexmin = [&](double ox, double oz) { if (ox < bx || (ox == bx && oz < bz)) { bx = ox; bz = oz; } };
-  for (int k = threadIdx.x; k < nsel; k += kThreads) lexmin(sm.x[k], sm.z[k]);   // NaN never compares less
+  int bi = -1;
+  auto lexmin = [&](double ox, double oz, int oi) {
+    if (oi < 0) return;
+    if (bi < 0 || ox < bx || (ox == bx && (oz < bz || (oz == bz && oi < bi)))) { bx = ox; bz = oz; bi = oi; }
+  };
+  for (int c = lane; c < nc; c += 32) {
+    const int k = sm.cand[c];
+    lexmin(sm.x[k], sm.z[k], k);
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lexmin(__shfl_xor_sync(kFull, bx, o), __shfl_xor_sync(kFull, bz, o));
-  __syncthreads();
-  if (lane == 0) { sm.red[warp][0] = bx; sm.red[warp][1] = bz; }
-  __syncthreads();
-  bx = sm.red[0][0]; bz = sm.red[0][1];
-#pragma unroll
-  for (int w = 1; w < kWarps; ++w) lexmin(sm.red[w][0], sm.red[w][1]);
+  for (int o = 16; o > 0; o >>= 1)
+    lexmin(__shfl_xor_sync(kFull, bx, o), __shfl_xor_sync(kFull, bz, o), __shfl_xor_sync(kFull, bi, o));
   const double sx0 = bx, sz0 = bz;
 
-  Wrap wr{sx0, sz0, sx0, sz0};
-  int hn = 0;
+  Wrap wr{sx0, sz0, 0.0, 0.0, -1};
+  int cur = bi, hn = 0;
   bool closed = false;
-  for (int step = 0; step < kMaxPts; ++step) {
-    if (threadIdx.x == 0) { sm.hx[hn] = wr.cx; sm.hz[hn] = wr.cz; }
+  for (int step = 0; step < kMaxPts && cur >= 0; ++step) {
+    if (lane == 0) sm.hull[hn] = (unsigned short)cur;
     ++hn;
-    wr.qx = wr.cx; wr.qz = wr.cz;
-    for (int k = threadIdx.x; k < nsel; k += kThreads) wr.offer(sm.x[k], sm.z[k]);
+    wr.qi = -1;
+    for (int c = lane; c < nc; c += 32) {
+      const int k = sm.cand[c];
+      wr.offer(sm.x[k], sm.z[k], k);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const double ox = __shfl_xor_sync(kFull, wr.qx, o), oz = __shfl_xor_sync(kFull, wr.qz, o);
-      wr.offer(ox, oz);
+      const int oi = __shfl_xor_sync(kFull, wr.qi, o);
+      wr.offer(ox, oz, oi);
     }
-    __syncthreads();
-    if (lane == 0) { sm.red[warp][0] = wr.qx; sm.red[warp][1] = wr.qz; }
-    __syncthreads();
-    wr.qx = sm.red[0][0]; wr.qz = sm.red[0][1];
-#pragma unroll
-    for (int w = 1; w < kWarps; ++w) wr.offer(sm.red[w][0], sm.red[w][1]);
-    if (wr.none()) break;                                          // every point coincides
-    if (wr.qx == sx0 && wr.qz == sz0) { closed = true; break; }    // wrapped around
-    wr.cx = wr.qx; wr.cz = wr.qz;
+    if (wr.qi < 0) break;                                           // every point coincides
+    if (wr.qx == sx0 && wr.qz == sz0) { closed = true; break; }     // wrapped around
+    wr.cx = wr.qx; wr.cz = wr.qz; cur = wr.qi;
   }
-  __syncthreads();
-  return (closed && hn >= 3) ? hn : 0;
+  if (lane == 0) sm.hull_n = (closed && hn >= 3) ? hn : 0;
 }
 
-// util_3dbox.py:202-218 over the hull edges.  The footprint is rotated by +yaw here
-// (rot_2d) although the box is later built with rotate_y(yaw) = -yaw in XZ: kept as is.
-// The extremes of a linear functional over the cloud are attained at hull vertices,
-// so only those are visited.
-__device__ double yaw_hull_edges(Smem& sm, int hn, double* areas) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int e = warp; e < hn; e += kWarps) {
-    const int e1 = (e + 1 == hn) ? 0 : e + 1;
-    const double ang = atan2(sm.hz[e1] - sm.hz[e], sm.hx[e1] - sm.hx[e]);
-    double s, c;
-    sincos(ang, &s, &c);
-    double mnx = CUDART_INF, mxx = -CUDART_INF, mnz = CUDART_INF, mxz = -CUDART_INF;
-    for (int k = lane; k < hn; k += 32) {
-      const double px = sm.hx[k], pz = sm.hz[k];
-      const double rx = c * px - s * pz, rz = s * px + c * pz;
-      mnx = fmin(mnx, rx); mxx = fmax(mxx, rx); mnz = fmin(mnz, rz); mxz = fmax(mxz, rz);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mnx = fmin(mnx, __shfl_xor_sync(kFull, mnx, o));
-      mxx = fmax(mxx, __shfl_xor_sync(kFull, mxx, o));
-      mnz = fmin(mnz, __shfl_xor_sync(kFull, mnz, o));
-      mxz = fmax(mxz, __shfl_xor_sync(kFull, mxz, o));
-    }
-    if (lane == 0) areas[e] = (mxx - mnx) * (mxz - mnz);
+// Bounding-rectangle area of the footprint (over an index list that contains every point that can
+// be extreme) after a rotation.  kind 0: the reference's
+// hull-edge test rotates by +ang (rot_2d of util_3dbox.py:206-210, kept although the box is
+// later built with rotate_y(yaw) = -yaw in XZ); kind 1: the sweep rotates like rotate_y(ang).
+__device__ __forceinline__ double rect_area(const Smem& sm, const unsigned short* list, int n, double ang, int kind) {
+  double s, c;
+  sincos(ang, &s, &c);
+  if (kind) s = -s;
+  double mnx = CUDART_INF, mxx = -CUDART_INF, mnz = CUDART_INF, mxz = -CUDART_INF;
+  for (int k = 0; k < n; ++k) {
+    const int idx = list[k];
+    const double px = sm.x[idx], pz = sm.z[idx];
+    const double rx = c * px - s * pz, rz = s * px + c * pz;
+    mnx = dmin(mnx, rx); mxx = dmax(mxx, rx); mnz = dmin(mnz, rz); mxz = dmax(mxz, rz);
   }
-  __syncthreads();
-  const int e = first_strict_min(areas, hn, sm);
-  if (e < 0) return 0.0;
-  const int e1 = (e + 1 == hn) ? 0 : e + 1;
-  return atan2(sm.hz[e1] - sm.hz[e], sm.hx[e1] - sm.hx[e]);
+  return (mxx - mnx) * (mxz - mnz);
+}
+
+__device__ __forceinline__ double edge_angle(const Smem& sm, int hn, int e) {
+  const int i0 = sm.hull[e], i1 = sm.hull[(e + 1 == hn) ? 0 : e + 1];
+  return atan2(sm.z[i1] - sm.z[i0], sm.x[i1] - sm.x[i0]);
+}
+
+__device__ __forceinline__ double sweep_angle(int c, int K) {
+  return __ddiv_rn(__dmul_rn((double)c, CUDART_PIO2), (double)K);     // k * (pi/2) / K as NumPy evaluates it
+}
+
+// ---- gather: rank -> pixel -> depth -> camera point ---------------------------------------
+// Branch-free binary search with a uniform step count, so that the searches of a thread's
+// samples interleave (independent shared-memory loads per step).
+template <int G>
+__device__ __forceinline__ void find_chunks(const uint32_t* pref, int chunks, int steps, const uint32_t (&r)[G],
+                                            int (&chunk)[G], uint32_t (&rem)[G]) {
+  int lo[G], hi[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) { lo[j] = 0; hi[j] = chunks; }    // invariant: pref[lo] <= r < pref[hi]
+  for (int s = 0; s < steps; ++s) {
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int mid = (lo[j] + hi[j]) >> 1;                     // == lo once the interval has closed
+      const bool right = pref[mid] <= r[j];
+      lo[j] = right ? mid : lo[j];
+      hi[j] = right ? hi[j] : mid;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < G; ++j) { chunk[j] = lo[j]; rem[j] = r[j] - pref[lo[j]]; }
 }
 
 // ---- the kernel ------------------------------------------------------------------------
 template <bool kScanned>
-__global__ void __launch_bounds__(kThreads) fit_kernel(FitArgs a) {
+__global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_raw[];
   __shared__ Smem sm;
   double* areas = reinterpret_cast<double*>(dyn_raw);                               // [n_areas]
-  uint32_t* pref = reinterpret_cast<uint32_t*>(dyn_raw + (size_t)a.n_areas * 8);    // [chunks+1], scanned source
+  unsigned char* region_b = dyn_raw + (size_t)a.n_areas * 8;
+  uint32_t* pref = reinterpret_cast<uint32_t*>(region_b);                           // [chunks+1], scanned source
+  if (threadIdx.x == 0) {
+    sm.rec = reinterpret_cast<double*>(region_b);                                   // used after pref is dead
+    sm.cand = reinterpret_cast<unsigned short*>(region_b + region_b_bytes(a.chunks, kScanned));
+    sm.hull = sm.cand + kMaxPts;
+  }
 
   const int box = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -359,14 +409,14 @@ __global__ void __launch_bounds__(kThreads) fit_kernel(FitArgs a) {
 
   long long n_src;
   const double* src_pts = nullptr;
+  const uint32_t* cc = nullptr;
   if (kScanned) {
-    n_src = a.counts[box];
-    // exclusive prefix over the chunk counts; each thread owns a contiguous run
-    const uint16_t* cc = a.chunk_counts + (size_t)box * a.chunks;
+    // exclusive prefix over the chunk totals; each thread owns a contiguous run
+    cc = a.chunk_counts + (size_t)box * a.chunks;
     const int per = (a.chunks + kThreads - 1) / kThreads;
     const int c_lo = min(tid * per, a.chunks), c_hi = min(c_lo + per, a.chunks);
     uint32_t run = 0;
-    for (int c = c_lo; c < c_hi; ++c) run += cc[c];
+    for (int c = c_lo; c < c_hi; ++c) run = __dp4a(__ldg(cc + c), 0x01010101u, run);
     uint32_t incl = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -377,14 +427,16 @@ __global__ void __launch_bounds__(kThreads) fit_kernel(FitArgs a) {
     __syncthreads();
     uint32_t base = incl - run;
     for (int w = 0; w < warp; ++w) base += (uint32_t)sm.ired[w][0];
-    for (int c = c_lo; c < c_hi; ++c) { pref[c] = base; base += cc[c]; }
+    for (int c = c_lo; c < c_hi; ++c) { pref[c] = base; base = __dp4a(__ldg(cc + c), 0x01010101u, base); }
     if (tid == kThreads - 1) pref[a.chunks] = base;
+    n_src = 0;
   } else {
     const long long o0 = a.offsets[box];
     n_src = a.offsets[box + 1] - o0;
     src_pts = a.pts + (size_t)o0 * 3;
   }
   __syncthreads();
+  if (kScanned) n_src = pref[a.chunks];        // = counts[box]
 
   const bool subsample = n_src > LA3D_SUBSAMPLE;
   int status = LA3D_ST_OK;
@@ -394,31 +446,95 @@ __global__ void __launch_bounds__(kThreads) fit_kernel(FitArgs a) {
   const int nsel = status ? 0 : (int)min((long long)LA3D_SUBSAMPLE, n_src);
 
   // ---- gather + lift + ground alignment + NaN-row filter ---------------------------
+  // The kGroup samples of a thread advance through the dependent loads together.
   int n_valid = 0, inf_xz = 0, inf_y = 0;
-  for (int k = tid; k < nsel; k += kThreads) {
-    double X, Y, Z;
+  double y_lo = CUDART_INF, y_hi = -CUDART_INF;
+  int search_steps = 0;
+  if (kScanned) while ((1 << search_steps) < a.chunks) ++search_steps;
+  for (int k0 = tid; k0 < nsel; k0 += kThreads * kGroup) {
+    double X[kGroup], Y[kGroup], Z[kGroup];
     if (kScanned) {
-      const uint32_t r = subsample ? (uint32_t)a.ranks[(size_t)box * LA3D_SUBSAMPLE + k] : (uint32_t)k;
-      const int p = select_pixel(a.bits + (size_t)box * a.chunks * kChunkWords, pref, a.chunks, r);
-      const float d = __ldg(a.depth + (size_t)img * a.HW + p);
-      const int v = p / a.W, u = p - v * a.W;
-      lift_pixel_exact((double)d, (double)u, (double)v, sm.Kinv, X, Y, Z);
+      uint32_t r[kGroup];
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) {
+        const int k = k0 + j * kThreads;
+        r[j] = (k < nsel && subsample) ? (uint32_t)__ldg(a.ranks + (size_t)box * LA3D_SUBSAMPLE + k) : (uint32_t)min(k, nsel - 1);
+      }
+      int chunk[kGroup];
+      uint32_t rem[kGroup];
+      find_chunks<kGroup>(pref, a.chunks, search_steps, r, chunk, rem);
+      uint32_t qw[kGroup];
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) qw[j] = __ldg(cc + chunk[j]);
+      uint4 w4[kGroup];
+      int base_px[kGroup];
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) {
+        // quarter of the chunk: byte q of qw = set pixels of its 128-pixel quarter q
+        int q = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t cnt = (qw[j] >> (8 * t)) & 0xffu;
+          const bool next = (q == t) && (rem[j] >= cnt);
+          rem[j] -= next ? cnt : 0u;
+          q += next ? 1 : 0;
+        }
+        base_px[j] = chunk[j] * kChunkPx + q * 128;
+        w4[j] = __ldg(reinterpret_cast<const uint4*>(a.bits + ((size_t)box * a.chunks + chunk[j]) * kChunkWords) + q);
+      }
+      float d[kGroup];
+      int p[kGroup];
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) {
+        const uint32_t w[4] = {w4[j].x, w4[j].y, w4[j].z, w4[j].w};
+        uint32_t word = w[0];
+        int wi = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t pc = __popc(w[t]);
+          const bool next = (wi == t) && (rem[j] >= pc);
+          rem[j] -= next ? pc : 0u;
+          wi += next ? 1 : 0;
+          word = next ? w[t + 1] : word;
+        }
+        p[j] = min(base_px[j] + wi * 32 + (int)__fns(word, 0, (int)rem[j] + 1), a.HW - 1);
+        d[j] = __ldg(a.depth + (size_t)img * a.HW + p[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) {
+        const int v = p[j] / a.W, u = p[j] - v * a.W;
+        lift_pixel_exact((double)d[j], (double)u, (double)v, sm.Kinv, X[j], Y[j], Z[j]);
+      }
     } else {
-      const long long row = subsample ? (long long)a.sample_idx[(size_t)box * LA3D_SUBSAMPLE + k] : (long long)k;
-      X = src_pts[row * 3]; Y = src_pts[row * 3 + 1]; Z = src_pts[row * 3 + 2];
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) {
+        const int k = k0 + j * kThreads;
+        X[j] = Y[j] = Z[j] = 0.0;
+        if (k < nsel) {
+          const long long row = subsample ? (long long)a.sample_idx[(size_t)box * LA3D_SUBSAMPLE + k] : (long long)k;
+          X[j] = src_pts[row * 3]; Y[j] = src_pts[row * 3 + 1]; Z[j] = src_pts[row * 3 + 2];
+        }
+      }
     }
-    // np.dot(in_pc, Rg): r_j = sum_i p_i Rg[i][j]  (inf * 0 -> NaN drops the row, as in NumPy)
-    double rx = X * sm.Rg[0] + Y * sm.Rg[3] + Z * sm.Rg[6];
-    const double ry = X * sm.Rg[1] + Y * sm.Rg[4] + Z * sm.Rg[7];
-    const double rz = X * sm.Rg[2] + Y * sm.Rg[5] + Z * sm.Rg[8];
-    if (isnan(rx) || isnan(ry) || isnan(rz)) {
-      rx = CUDART_NAN;
-    } else {
-      ++n_valid;
-      inf_xz |= (int)(isinf(rx) || isinf(rz));
-      inf_y |= (int)isinf(ry);
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) {
+      const int k = k0 + j * kThreads;
+      if (k < nsel) {
+        // np.dot(in_pc, Rg): r_j = sum_i p_i Rg[i][j]  (inf * 0 -> NaN drops the row, as in NumPy)
+        double rx = X[j] * sm.Rg[0] + Y[j] * sm.Rg[3] + Z[j] * sm.Rg[6];
+        const double ry = X[j] * sm.Rg[1] + Y[j] * sm.Rg[4] + Z[j] * sm.Rg[7];
+        const double rz = X[j] * sm.Rg[2] + Y[j] * sm.Rg[5] + Z[j] * sm.Rg[8];
+        if (isnan(rx) || isnan(ry) || isnan(rz)) {
+          rx = CUDART_NAN;
+        } else {
+          ++n_valid;
+          inf_xz |= (int)(isinf(rx) || isinf(rz));
+          inf_y |= (int)isinf(ry);
+          y_lo = dmin(y_lo, ry); y_hi = dmax(y_hi, ry);
+        }
+        sm.x[k] = rx; sm.z[k] = rz;
+      }
     }
-    sm.x[k] = rx; sm.y[k] = ry; sm.z[k] = rz;
   }
   {
     int r[3] = {n_valid, inf_xz, inf_y};
@@ -434,50 +550,75 @@ __global__ void __launch_bounds__(kThreads) fit_kernel(FitArgs a) {
   }
 
   if (status != LA3D_ST_OK) {                          // uniform across the CTA
-    if (tid < LA3D_REC) {
+    for (int f = tid; f < LA3D_REC; f += kThreads) {
       double val = CUDART_NAN;
-      if (tid == LA3D_O_NVALID) val = (double)n_valid;
-      if (tid == LA3D_O_STATUS) val = (double)status;
-      if (tid == LA3D_O_NMASK) val = (double)n_src;
-      if (tid == LA3D_O_PAD) val = 0.0;
-      if (a.rec_f64) reinterpret_cast<double*>(a.records)[(size_t)box * LA3D_REC + tid] = val;
-      else reinterpret_cast<float*>(a.records)[(size_t)box * LA3D_REC + tid] = (float)val;
+      if (f == LA3D_O_NVALID) val = (double)n_valid;
+      if (f == LA3D_O_STATUS) val = (double)status;
+      if (f == LA3D_O_NMASK) val = (double)n_src;
+      if (f == LA3D_O_PAD) val = 0.0;
+      if (a.rec_f64) reinterpret_cast<double*>(a.records)[(size_t)box * LA3D_REC + f] = val;
+      else reinterpret_cast<float*>(a.records)[(size_t)box * LA3D_REC + f] = (float)val;
     }
     return;
   }
 
   // ---- yaw ---------------------------------------------------------------------------
-  double yaw;
-  if (a.method == LA3D_METHOD_SWEEP) {
-    yaw = yaw_sweep(sm, nsel, a.yaw_steps, areas, inf_y != 0);
+  bool have_trig = false;          // yaw_pca leaves cos / sin of the yaw in shared memory
+  if (a.method == LA3D_METHOD_PCA) {
+    yaw_pca(sm, nsel, n_valid);
+    have_trig = true;
   } else {
-    int hn = 0;
-    if (a.method == LA3D_METHOD_CONVEX_HULL) hn = hull_wrap(sm, nsel);
-    yaw = hn ? yaw_hull_edges(sm, hn, areas) : yaw_pca(sm, nsel, n_valid);
+    octagon_candidates(sm, nsel);
+    const int nc = sm.cand_n;
+    if (a.method == LA3D_METHOD_CONVEX_HULL) {
+      if (warp == 0) hull_wrap(sm);
+      __syncthreads();
+      const int hn = sm.hull_n;
+      if (hn == 0) {
+        yaw_pca(sm, nsel, n_valid);                    // Qhull would have raised (QH6214 / QH6154): fall back
+        have_trig = true;
+      } else {
+        // util_3dbox.py:202-218: one thread per hull edge, first strict minimum of the area
+        for (int e = tid; e < hn; e += kThreads) areas[e] = rect_area(sm, sm.hull, hn, edge_angle(sm, hn, e), 0);
+        __syncthreads();
+        const int e = first_strict_min(areas, hn, sm);
+        if (tid == 0) sm.yaw = e < 0 ? 0.0 : edge_angle(sm, hn, e);
+      }
+    } else {
+      // uniform sweep: yaw_k = k*(pi/2)/K, first strict minimum of dx*dz
+      const int K = a.yaw_steps;
+      if (inf_y) {
+        if (tid == 0) sm.yaw = 0.0;                    // 0*inf = NaN in every area: nothing beats +inf
+      } else {
+        for (int c = tid; c < K; c += kThreads) areas[c] = rect_area(sm, sm.cand, nc, sweep_angle(c, K), 1);
+        __syncthreads();
+        const int c = first_strict_min(areas, K, sm);
+        if (tid == 0) sm.yaw = c < 0 ? 0.0 : sweep_angle(c, K);
+      }
+    }
   }
+  __syncthreads();
+  const double yaw = sm.yaw;
 
   // ---- extents at that yaw: rotate_y(yaw) @ pc^T, per-axis min / max (:154-160) ------
   double sy_, cy_;
-  sincos(yaw, &sy_, &cy_);
-  double lo[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, hi[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+  if (have_trig) { sy_ = sm.sin_yaw; cy_ = sm.cos_yaw; }
+  else sincos(yaw, &sy_, &cy_);
+  double ext[6] = {CUDART_INF, y_lo, CUDART_INF, -CUDART_INF, y_hi, -CUDART_INF};
   for (int k = tid; k < nsel; k += kThreads) {
-    const double px = sm.x[k], py = sm.y[k], pz = sm.z[k];
-    if (px == px) {
-      const double rx = cy_ * px + sy_ * pz, rz = cy_ * pz - sy_ * px;
-      lo[0] = fmin(lo[0], rx); hi[0] = fmax(hi[0], rx);
-      lo[1] = fmin(lo[1], py); hi[1] = fmax(hi[1], py);
-      lo[2] = fmin(lo[2], rz); hi[2] = fmax(hi[2], rz);
-    }
+    const double px = sm.x[k], pz = sm.z[k];         // a dropped row is NaN in x and loses every comparison
+    const double rx = cy_ * px + sy_ * pz, rz = cy_ * pz - sy_ * px;
+    ext[0] = dmin(ext[0], rx); ext[3] = dmax(ext[3], rx);
+    ext[2] = dmin(ext[2], rz); ext[5] = dmax(ext[5], rz);
   }
-  block_reduce(lo, sm, OpMin());
-  block_reduce(hi, sm, OpMax());
-  if (inf_y) { lo[0] = hi[0] = lo[2] = hi[2] = CUDART_NAN; }      // 0 * inf in the x / z rows of the product
-  const double dim[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
-  const double ctr[3] = {(lo[0] + hi[0]) / 2, (lo[1] + hi[1]) / 2, (lo[2] + hi[2]) / 2};
+  block_reduce(ext, sm, OpMinMax());
+  if (inf_y) { ext[0] = ext[3] = ext[2] = ext[5] = CUDART_NAN; }      // 0 * inf in the x / z rows of the product
+  const double dim[3] = {ext[3] - ext[0], ext[4] - ext[1], ext[5] - ext[2]};
+  const double ctr[3] = {(ext[0] + ext[3]) / 2, (ext[1] + ext[4]) / 2, (ext[2] + ext[5]) / 2};
 
+  double* rec = sm.rec;
   // rotate_y(-yaw) = [[c,0,-s],[0,1,0],[s,0,c]] with c = cos(yaw), s = sin(yaw)
   const double Ry[9] = {cy_, 0.0, -sy_, 0.0, 1.0, 0.0, sy_, 0.0, cy_};
-  __syncthreads();
   if (tid < 8) {
     // convert_box_vertices(cx,cy,cz,dx,dy,dz,0).astype(float16)  (:71-103, :165)
     const double sgx = (tid == 1 || tid == 2 || tid == 5 || tid == 6) ? 1.0 : -1.0;
@@ -498,7 +639,7 @@ __global__ void __launch_bounds__(kThreads) fit_kernel(FitArgs a) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) v2[i] = v1[0] * sm.Rg[i * 3] + v1[1] * sm.Rg[i * 3 + 1] + v1[2] * sm.Rg[i * 3 + 2];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) sm.rec[LA3D_O_VERT + tid * 3 + i] = v2[i];
+    for (int i = 0; i < 3; ++i) rec[LA3D_O_VERT + tid * 3 + i] = v2[i];
     // project_to_2d (util.py:227-229)
     double uu = CUDART_NAN, vv = CUDART_NAN;
     if (a.K) {
@@ -507,55 +648,57 @@ __global__ void __launch_bounds__(kThreads) fit_kernel(FitArgs a) {
       const double h2 = sm.Kmat[6] * v2[0] + sm.Kmat[7] * v2[1] + sm.Kmat[8] * v2[2];
       uu = h0 / h2; vv = h1 / h2;
     }
-    sm.rec[LA3D_O_UV + tid * 2] = uu;
-    sm.rec[LA3D_O_UV + tid * 2 + 1] = vv;
+    rec[LA3D_O_UV + tid * 2] = uu;
+    rec[LA3D_O_UV + tid * 2 + 1] = vv;
   } else if (tid == 32) {
     // center_cam = Rg^T @ (rotate_y(-yaw) @ c)  (:172-173; Rg^T where the corners used Rg - kept)
     double w[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) w[i] = Ry[i * 3] * ctr[0] + Ry[i * 3 + 1] * ctr[1] + Ry[i * 3 + 2] * ctr[2];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) sm.rec[LA3D_O_CENTER + i] = sm.Rg[i] * w[0] + sm.Rg[3 + i] * w[1] + sm.Rg[6 + i] * w[2];
-    sm.rec[LA3D_O_DIM] = dim[2]; sm.rec[LA3D_O_DIM + 1] = dim[1]; sm.rec[LA3D_O_DIM + 2] = dim[0];
-    sm.rec[LA3D_O_YAW] = yaw;
-    sm.rec[LA3D_O_NVALID] = (double)n_valid;
-    sm.rec[LA3D_O_STATUS] = (double)LA3D_ST_OK;
-    sm.rec[LA3D_O_NMASK] = (double)n_src;
-    sm.rec[LA3D_O_PAD] = 0.0;
-  } else if (tid == 64) {
+    for (int i = 0; i < 3; ++i) rec[LA3D_O_CENTER + i] = sm.Rg[i] * w[0] + sm.Rg[3 + i] * w[1] + sm.Rg[6 + i] * w[2];
+    rec[LA3D_O_DIM] = dim[2]; rec[LA3D_O_DIM + 1] = dim[1]; rec[LA3D_O_DIM + 2] = dim[0];
+    rec[LA3D_O_YAW] = yaw;
+    rec[LA3D_O_NVALID] = (double)n_valid;
+    rec[LA3D_O_STATUS] = (double)LA3D_ST_OK;
+    rec[LA3D_O_NMASK] = (double)n_src;
+    rec[LA3D_O_PAD] = 0.0;
+  } else if (tid == 40) {
     // R_cam = Rg^T @ rotate_y(-yaw)  (:176)
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int k = 0; k < 3; ++k)
-        sm.rec[LA3D_O_RCAM + i * 3 + k] = sm.Rg[i] * Ry[k] + sm.Rg[3 + i] * Ry[3 + k] + sm.Rg[6 + i] * Ry[6 + k];
+        rec[LA3D_O_RCAM + i * 3 + k] = sm.Rg[i] * Ry[k] + sm.Rg[3 + i] * Ry[3 + k] + sm.Rg[6 + i] * Ry[6 + k];
   }
   __syncthreads();
   if (tid == 0) {
     // Python min()/max() over the 8 projections (combine_results.py:241-246): sequential
     // `if x < m` / `if x > m`, so a leading NaN sticks and a later NaN is skipped.
-    double mnu = sm.rec[LA3D_O_UV], mnv = sm.rec[LA3D_O_UV + 1], mxu = mnu, mxv = mnv;
+    double mnu = rec[LA3D_O_UV], mnv = rec[LA3D_O_UV + 1], mxu = mnu, mxv = mnv;
     for (int j = 1; j < 8; ++j) {
-      const double uu = sm.rec[LA3D_O_UV + 2 * j], vv = sm.rec[LA3D_O_UV + 2 * j + 1];
+      const double uu = rec[LA3D_O_UV + 2 * j], vv = rec[LA3D_O_UV + 2 * j + 1];
       if (uu < mnu) mnu = uu;
       if (vv < mnv) mnv = vv;
       if (uu > mxu) mxu = uu;
       if (vv > mxv) mxv = vv;
     }
-    sm.rec[LA3D_O_BOX2D] = mnu; sm.rec[LA3D_O_BOX2D + 1] = mnv;
-    sm.rec[LA3D_O_BOX2D + 2] = mxu; sm.rec[LA3D_O_BOX2D + 3] = mxv;
+    rec[LA3D_O_BOX2D] = mnu; rec[LA3D_O_BOX2D + 1] = mnv;
+    rec[LA3D_O_BOX2D + 2] = mxu; rec[LA3D_O_BOX2D + 3] = mxv;
   }
   __syncthreads();
-  if (tid < LA3D_REC) {
-    if (a.rec_f64) reinterpret_cast<double*>(a.records)[(size_t)box * LA3D_REC + tid] = sm.rec[tid];
-    else reinterpret_cast<float*>(a.records)[(size_t)box * LA3D_REC + tid] = (float)sm.rec[tid];
+  for (int f = tid; f < LA3D_REC; f += kThreads) {
+    if (a.rec_f64) reinterpret_cast<double*>(a.records)[(size_t)box * LA3D_REC + f] = rec[f];
+    else reinterpret_cast<float*>(a.records)[(size_t)box * LA3D_REC + f] = (float)rec[f];
   }
 }
 
 int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s) {
-  a.n_areas = a.method == LA3D_METHOD_SWEEP ? (a.yaw_steps > 0 ? a.yaw_steps : 1) : kMaxPts;
-  a.n_areas = (a.n_areas + 1) & ~1;                       // keep pref 16-byte aligned
-  const size_t dyn = (size_t)a.n_areas * 8 + (scanned ? ((size_t)a.chunks + 1) * 4 : 0);
+  a.n_areas = a.method == LA3D_METHOD_SWEEP ? (a.yaw_steps > 0 ? a.yaw_steps : 1)
+            : a.method == LA3D_METHOD_CONVEX_HULL ? kMaxPts : 0;
+  a.n_areas = (a.n_areas + 1) & ~1;                       // keep what follows 16-byte aligned
+  const size_t lists = a.method == LA3D_METHOD_PCA ? 0 : (size_t)kMaxPts * 2 * (a.method == LA3D_METHOD_SWEEP ? 1 : 2);
+  const size_t dyn = (size_t)a.n_areas * 8 + region_b_bytes(a.chunks, scanned) + lists;
   if (dyn + sizeof(Smem) > 227 * 1024) {
     set_error("la3d fit: image or yaw sweep too large for shared memory (%zu bytes needed)", dyn + sizeof(Smem));
     return LA3D_EINVAL;
@@ -575,7 +718,7 @@ int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s) {
 }  // namespace la3d
 
 extern "C" int la3d_fit_scanned(const float* depth, const double* K, const double* ground, const uint32_t* bits,
-                                const uint16_t* chunk_counts, const int32_t* counts, const int32_t* ranks, int B,
+                                const uint32_t* chunk_counts, const int32_t* counts, const int32_t* ranks, int B,
                                 int I, int H, int W, int method, int yaw_steps, void* records, int rec_f64,
                                 la3d_stream_t stream) {
   using namespace la3d;

@@ -1,8 +1,9 @@
 // Mask-stack scan on sm_100a: byte masks -> bit masks + per-chunk popcounts.
 //
 // This is the HBM-bound pass of the box-fitting path: it reads every mask byte
-// exactly once (I bytes per pixel) and writes 1/8 of that back as bits plus two
-// bytes per 512 pixels.  Everything downstream (counts, the row-major rank
+// exactly once (I bytes per pixel) and writes 1/8 of that back as bits plus four
+// bytes per 512 pixels (the set-pixel counts of the chunk's four 128-pixel quarters,
+// one byte each - a quarter holds at most 128 = 0x80, so the bytes never carry).  Everything downstream (counts, the row-major rank
 // select that stands in for NumPy's pts[mask], mask statistics) works on the
 // bit planes.  Integer work: results are exact.
 //
@@ -54,7 +55,7 @@ template <bool k01, bool kVec>
 __global__ void __launch_bounds__(kThreads) mask_scan_kernel(const uint8_t* __restrict__ masks, int HW,
                                                              int chunks_per_plane, int tiles_per_plane,
                                                              uint32_t* __restrict__ bits,
-                                                             uint16_t* __restrict__ chunk_counts) {
+                                                             uint32_t* __restrict__ chunk_counts) {
   const int plane = blockIdx.x / tiles_per_plane;
   const int tile = blockIdx.x - plane * tiles_per_plane;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,16 +78,17 @@ __global__ void __launch_bounds__(kThreads) mask_scan_kernel(const uint8_t* __re
   }
 
   uint32_t* dst_bits = bits + (size_t)plane * chunks_per_plane * kChunkWords;
-  uint16_t* dst_cnt = chunk_counts + (size_t)plane * chunks_per_plane;
+  uint32_t* dst_cnt = chunk_counts + (size_t)plane * chunks_per_plane;
 #pragma unroll
   for (int j = 0; j < kUnroll; ++j) {
     const int c = c0 + j;
     if (c >= chunks_per_plane) break;                       // warp-uniform
     const uint32_t half = pack16<k01>(q[j]);
     const uint32_t other = __shfl_xor_sync(0xffffffffu, half, 1);
-    const uint32_t total = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(half));
+    // lanes 8q..8q+7 hold quarter q: one warp reduction yields all four byte counts
+    const uint32_t quarters = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(half) << (8 * (lane >> 3)));
     if ((lane & 1) == 0) dst_bits[c * kChunkWords + (lane >> 1)] = half | (other << 16);
-    if (lane == 0) dst_cnt[c] = (uint16_t)total;
+    if (lane == 0) dst_cnt[c] = quarters;
   }
 }
 
@@ -99,7 +101,7 @@ extern "C" size_t la3d_chunks_per_plane(int H, int W) {
 extern "C" size_t la3d_words_per_plane(int H, int W) { return la3d_chunks_per_plane(H, W) * la3d::kChunkWords; }
 
 extern "C" int la3d_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
-                              uint16_t* chunk_counts, la3d_stream_t stream) {
+                              uint32_t* chunk_counts, la3d_stream_t stream) {
   using namespace la3d;
   LA3D_REQUIRE(masks && bits && chunk_counts, "null pointer");
   LA3D_REQUIRE(planes > 0 && H > 0 && W > 0, "non-positive shape");

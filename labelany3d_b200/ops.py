@@ -90,11 +90,11 @@ def scan_layout(H, W):
 
 
 def mask_scan(masks):
-    """``masks[..., H, W]`` (bool / uint8) -> ``(bits[P, words] int32, chunk_counts[P, chunks] int16)``.
+    """``masks[..., H, W]`` (bool / uint8) -> ``(bits[P, words] int32, chunk_counts[P, chunks] int32)``.
 
     ``P`` = product of the leading dimensions.  Bit ``k`` of word ``w`` of a plane is
-    pixel ``32 w + k`` in row-major order; ``chunk_counts`` holds the set pixels of every
-    512-pixel chunk (as unsigned 16-bit values stored in an int16 tensor).
+    pixel ``32 w + k`` in row-major order; a ``chunk_counts`` word packs the set-pixel counts
+    of the four 128-pixel quarters of a 512-pixel chunk, one byte each (byte 0 = first quarter).
     """
     lib = _lib.load()
     masks = _need_cuda("masks", masks)
@@ -103,7 +103,7 @@ def mask_scan(masks):
     planes = masks.numel() // (H * W)
     chunks, words = scan_layout(H, W)
     bits = torch.empty((planes, words), dtype=torch.int32, device=masks.device)
-    cc = torch.empty((planes, chunks), dtype=torch.int16, device=masks.device)
+    cc = torch.empty((planes, chunks), dtype=torch.int32, device=masks.device)
     with torch.cuda.device(masks.device):
         rc = lib.la3d_mask_scan(_ptr(m8), planes, H, W, is01, _ptr(bits), _ptr(cc), _stream())
     _lib.check(rc, "la3d_mask_scan")
@@ -117,7 +117,7 @@ def sample_ranks(chunk_counts, B, I, H, W, seed=0, image_offset=0):
     most 500 pixels are left at -1 (the reference keeps all their points).
     """
     lib = _lib.load()
-    cc = _need_cuda("chunk_counts", chunk_counts, torch.int16)
+    cc = _need_cuda("chunk_counts", chunk_counts, torch.int32)
     counts = torch.empty((B, I), dtype=torch.int32, device=cc.device)
     ranks = torch.full((B, I, SUBSAMPLE), -1, dtype=torch.int32, device=cc.device)
     with torch.cuda.device(cc.device):
@@ -198,7 +198,7 @@ class BoxFitter:
         up = lambda v: (v + 255) & ~255  # noqa: E731
         base = self.workspace.data_ptr()
         o_cc = up(planes * words * 4)
-        o_counts = up(o_cc + planes * chunks * 2)
+        o_counts = up(o_cc + planes * chunks * 4)
         o_ranks = up(o_counts + planes * 4)
         assert up(o_ranks + planes * SUBSAMPLE * 4) == self.ws_bytes
         return base, base + o_cc, base + o_counts, base + o_ranks

@@ -110,8 +110,9 @@ def test_mask_scan_exact(ops, shape, kind):
     flat[:, :H * W] = m.reshape(planes, -1)
     want_bits = np.packbits(flat, axis=1, bitorder="little").view(np.uint32)
     np.testing.assert_array_equal(bits.cpu().numpy().view(np.uint32), want_bits)
-    want_cc = flat.reshape(planes, chunks, 512).sum(-1)
-    np.testing.assert_array_equal(cc.cpu().numpy().view(np.uint16), want_cc)
+    want_cc = flat.reshape(planes, chunks, 4, 128).sum(-1).astype(np.uint8)       # four quarter counts per chunk ...
+    got_cc = cc.cpu().numpy().view(np.uint8).reshape(planes, chunks, 4)           # ... one byte each, little-endian
+    np.testing.assert_array_equal(got_cc, want_cc)
     counts, _ = ops.sample_ranks(cc, shape[0], shape[1], H, W, seed=1)
     np.testing.assert_array_equal(counts.cpu().numpy(), orc.mask_counts(m))
 
@@ -121,12 +122,12 @@ def test_legacy_randint_stream(ops, golden):
     H, W = 384, 385
     chunks, _ = ops.scan_layout(H, W)
     for i, (seed, high) in enumerate(golden["rng/cases"]):
-        cc = np.zeros((2, chunks), dtype=np.int64)
+        cc = np.zeros((2, chunks, 4), dtype=np.uint8)          # the sampler only totals the quarter bytes
         for row, n in enumerate((int(high), int(high) + 3)):
-            full, rest = divmod(n, 512)
-            cc[row, :full] = 512
-            cc[row, full] = rest
-        counts, ranks = ops.sample_ranks(dev(cc.astype(np.uint16).view(np.int16)), 1, 2, H, W, seed=int(seed))
+            full, rest = divmod(n, 128)
+            cc[row].reshape(-1)[:full] = 128
+            cc[row].reshape(-1)[full] = rest
+        counts, ranks = ops.sample_ranks(dev(cc.view(np.int32).reshape(2, chunks)), 1, 2, H, W, seed=int(seed))
         assert counts.cpu().numpy().tolist() == [[int(high), int(high) + 3]]
         got = ranks.cpu().numpy()[0]
         if high > 500:
@@ -137,9 +138,9 @@ def test_legacy_randint_stream(ops, golden):
             np.testing.assert_array_equal(got[1], np.random.RandomState(int(seed)).randint(0, high + 3, 500)
                                           if high + 3 > 500 else got[1])
     # seed + image_offset wraps mod 2**32 like np.random.seed requires
-    cc = np.zeros((1, chunks), dtype=np.uint16)
-    cc[0, :4] = 512
-    _, r = ops.sample_ranks(dev(cc.view(np.int16)), 1, 1, H, W, seed=2 ** 32 - 1, image_offset=3)
+    cc = np.zeros((1, chunks, 4), dtype=np.uint8)
+    cc[0, :4] = 128
+    _, r = ops.sample_ranks(dev(cc.view(np.int32).reshape(1, chunks)), 1, 1, H, W, seed=2 ** 32 - 1, image_offset=3)
     np.testing.assert_array_equal(r.cpu().numpy()[0, 0], np.random.RandomState(2).randint(0, 2048, 500))
 
 

@@ -51,7 +51,7 @@ def main():
     m8 = masks.view(torch.uint8)
     chunks, words = ops.scan_layout(H, W)
     bits = torch.empty((B * I, words), dtype=torch.int32, device="cuda")
-    cc = torch.empty((B * I, chunks), dtype=torch.int16, device="cuda")
+    cc = torch.empty((B * I, chunks), dtype=torch.int32, device="cuda")
     for is01 in (1, 0):
         med, best = timeit(lambda: lib.la3d_mask_scan(m8.data_ptr(), B * I, H, W, is01, bits.data_ptr(), cc.data_ptr(), st))
         out[f"scan{is01}_ms"] = med; out[f"scan{is01}_GBs"] = px * I / med / 1e6; out[f"scan{is01}_best_GBs"] = px * I / best / 1e6

@@ -19,7 +19,7 @@ st = torch.cuda.current_stream().cuda_stream
 m8 = masks.view(torch.uint8)
 chunks, words = ops.scan_layout(H, W)
 bits = torch.empty((B * I, words), dtype=torch.int32, device="cuda")
-cc = torch.empty((B * I, chunks), dtype=torch.int16, device="cuda")
+cc = torch.empty((B * I, chunks), dtype=torch.int32, device="cuda")
 counts = torch.empty((B, I), dtype=torch.int32, device="cuda")
 ranks = torch.empty((B, I, 500), dtype=torch.int32, device="cuda")
 rec = torch.empty((B, I, 64), dtype=torch.float64, device="cuda")
