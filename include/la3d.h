@@ -130,11 +130,23 @@ int la3d_fit_scanned(const float* depth, const double* K, const double* ground, 
                      const uint32_t* chunk_counts, const int32_t* counts, const int32_t* ranks, int B, int I, int H,
                      int W, int method, int yaw_steps, void* records, int rec_f64, la3d_stream_t stream);
 
-/* The three calls above back to back.  `workspace` needs la3d_fit_workspace_bytes(). */
+/* The three calls above as one pipeline.  `workspace` needs la3d_fit_workspace_bytes().
+ * With the environment variable LA3D_PARTS=n (n > 1; experimental, off by default because it
+ * measured slower on B200) the batch is cut into n parts: the scans of all parts run back to back
+ * on `stream`, the sampler and fit kernel of a part run on an internal high-priority stream as
+ * soon as that part is scanned, and `stream` waits for them before the call returns - to the
+ * caller the call is still one asynchronous operation on `stream`, with identical results. */
 size_t la3d_fit_workspace_bytes(int B, int I, int H, int W);
 int la3d_fit_boxes(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
                    int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed, uint32_t image_offset,
                    void* workspace, size_t workspace_bytes, void* records, int rec_f64, la3d_stream_t stream);
+
+/* Optional timing of the scans inside la3d_fit_boxes: after la3d_set_profiling(1), every call
+ * brackets the mask scan of each part with timing events on `stream`; once the stream has been
+ * synchronised, la3d_last_scan_ms() writes the per-part durations (ms) of the last call on this
+ * device and returns how many parts there were (0 when the call ran unsplit), or a negative code. */
+void la3d_set_profiling(int on);
+int la3d_last_scan_ms(float* ms, int max_parts);
 
 /* ---------------------------------------------------------------------------
  * Oriented box from explicit point sets.  Replaces estimate_bbox,

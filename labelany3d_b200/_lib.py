@@ -26,6 +26,8 @@ SIGNATURES = {
     "la3d_fit_boxes": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _i, _vp]),
     "la3d_fit_points": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "la3d_project_points": (_i, [_vp, _vp, _vp, C.c_longlong, _vp, _vp]),
+    "la3d_set_profiling": (None, [_i]),
+    "la3d_last_scan_ms": (_i, [_vp, _i]),
 }
 
 _lib = None

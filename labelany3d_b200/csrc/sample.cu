@@ -71,8 +71,28 @@ __device__ __forceinline__ void mt_next_block(uint32_t* mt, uint32_t* out) {
   __syncthreads();
 }
 
+// init_genrand for one image per warp (lane 0 runs the recurrence, the warp stores the state).
+// Launched ahead of the mask scan so that the serial part of seeding is off the critical path.
+__global__ void __launch_bounds__(kThreads) seed_kernel(int B, uint32_t seed0, uint32_t* __restrict__ states) {
+  __shared__ uint32_t st[kWarps][kMtN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kWarps + warp;
+  if (b >= B) return;
+  if (lane == 0) {
+    uint32_t s = seed0 + (uint32_t)b;
+#pragma unroll 8
+    for (int i = 0; i < kMtN; ++i) {
+      st[warp][i] = s;
+      s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
+    }
+  }
+  __syncwarp();
+  for (int k = lane; k < kMtN; k += 32) states[(size_t)b * kMtN + k] = st[warp][k];
+}
+
 __global__ void __launch_bounds__(kThreads) sample_kernel(const uint32_t* __restrict__ chunk_counts, int I, int chunks,
-                                                          uint32_t seed0, int32_t* __restrict__ counts,
+                                                          uint32_t seed0, const uint32_t* __restrict__ states,
+                                                          int32_t* __restrict__ counts,
                                                           int32_t* __restrict__ ranks) {
   __shared__ uint32_t mt[kMtN], out[kMtN];
   __shared__ int wtot[kWarps], end_pos;
@@ -80,8 +100,11 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const uint32_t* __rest
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x;
 
+  if (states) {
+    for (int k = tid; k < kMtN; k += kThreads) mt[k] = __ldg(states + (size_t)b * kMtN + k);   // seeded earlier
+  }
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && !states) {
       uint32_t s = seed0 + (uint32_t)b;       // mod 2^32, as np.random.seed requires
 #pragma unroll 8
       for (int i = 0; i < kMtN; ++i) {
@@ -170,7 +193,22 @@ extern "C" int la3d_sample_ranks(const uint32_t* chunk_counts, int B, int I, int
   LA3D_REQUIRE(I <= 8192, "at most 8192 instances per image");
   const int chunks = (int)la3d_chunks_per_plane(H, W);
   sample_kernel<<<(unsigned)B, kThreads, (size_t)I * 4, static_cast<cudaStream_t>(stream)>>>(
-      chunk_counts, I, chunks, seed + image_offset, counts, ranks);
+      chunk_counts, I, chunks, seed + image_offset, nullptr, counts, ranks);
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
 }
+
+namespace la3d {
+// Internal (pipeline in api.cu): seeding split from sampling.
+int seed_states(int B, uint32_t seed0, uint32_t* states, cudaStream_t s) {
+  seed_kernel<<<(unsigned)((B + kWarps - 1) / kWarps), kThreads, 0, s>>>(B, seed0, states);
+  LA3D_CUDA(cudaGetLastError());
+  return LA3D_OK;
+}
+int sample_seeded(const uint32_t* chunk_counts, int B, int I, int chunks, const uint32_t* states, int32_t* counts,
+                  int32_t* ranks, cudaStream_t s) {
+  sample_kernel<<<(unsigned)B, kThreads, (size_t)I * 4, s>>>(chunk_counts, I, chunks, 0u, states, counts, ranks);
+  LA3D_CUDA(cudaGetLastError());
+  return LA3D_OK;
+}
+}  // namespace la3d

@@ -190,6 +190,26 @@ class BoxFitter:
                 events[3].record()
         return rec
 
+    def capture(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0, out=None):
+        """Record one call as a CUDA graph and return its ``replay()``: the kernels of a step (and
+        the stream fork / join of the pipelined path) are then launched by one ``cudaGraphLaunch``
+        instead of a dozen driver calls.  The graph reads the SAME buffers on every replay: refill
+        ``depth`` / ``K`` / ``masks`` / ``ground`` in place to process new data.  Returns
+        ``(replay, records)``."""
+        rec = self.records if out is None else out
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):                     # warm-up outside capture (lazy driver state, side streams)
+                self(depth, K, masks, ground, method, yaw_steps, seed, image_offset, out=rec)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self(depth, K, masks, ground, method, yaw_steps, seed, image_offset, out=rec)
+        self._graph_keepalive = (graph, depth, K, masks, ground, rec)
+        return graph.replay, rec
+
     def _carve(self):
         """Workspace sub-buffers in the order ``la3d_fit_boxes`` lays them out (256-byte aligned)."""
         B, I, H, W = self.shape
@@ -200,7 +220,7 @@ class BoxFitter:
         o_cc = up(planes * words * 4)
         o_counts = up(o_cc + planes * chunks * 4)
         o_ranks = up(o_counts + planes * 4)
-        assert up(o_ranks + planes * SUBSAMPLE * 4) == self.ws_bytes
+        assert up(up(o_ranks + planes * SUBSAMPLE * 4) + B * 624 * 4) == self.ws_bytes
         return base, base + o_cc, base + o_counts, base + o_ranks
 
 
