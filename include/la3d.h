@@ -106,47 +106,57 @@ int la3d_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_0
                    uint32_t* chunk_counts, la3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Mask-independent preparation of a batch for the scanned-mask path.  Everything the
+ * sampler and the fit kernel need that does not depend on the masks, so that it can run
+ * concurrently with the mask scan (la3d_fit_boxes folds it into the scan's launch):
+ *   - per image b, NumPy's legacy MT19937 seeded with (seed + image_offset + b) mod 2^32
+ *     (np.random.seed) and its first words pre-generated, plus the state to continue from;
+ *   - per image, the intrinsics and their inverse (np.linalg.inv(K), src/util.py:56);
+ *   - per box, the ground rotation Rg of src/util_3dbox.py:128-134.
+ *   K [B][9] double intrinsics; ground nullable [B*I][3] double
+ *   prep: la3d_prep_bytes(B, I) bytes, 256-byte aligned (opaque)
+ * la3d_set_mt_blocks(n): tuning / test hook - pre-generate n blocks of 624 words per image
+ * instead of the automatic ceil(I*1024/624)+1 (0 restores the automatic choice).  Results
+ * never depend on it (the sampler continues the generator when the words run out); it must
+ * not change between la3d_prep_bytes / la3d_fit_prepare and the calls that consume `prep`.
+ * ------------------------------------------------------------------------- */
+size_t la3d_prep_bytes(int B, int I);
+int la3d_fit_prepare(const double* K, const double* ground, int B, int I, uint32_t seed, uint32_t image_offset,
+                     void* prep, size_t prep_bytes, la3d_stream_t stream);
+void la3d_set_mt_blocks(int n);
+
+/* ---------------------------------------------------------------------------
  * Per-image subsample ranks.  Replaces `np.random.randint(0, N, 500)` of
- * src/util_3dbox.py:123-125 for a whole batch: image b re-seeds NumPy's legacy
- * MT19937 with (seed + image_offset + b) mod 2^32 and its instances draw from
- * that stream in order, each only if its count N exceeds 500 (masked rejection
- * on 32-bit draws, exactly RandomState.randint).
+ * src/util_3dbox.py:123-125 for a whole batch: the instances of image b draw from
+ * that image's stream (see la3d_fit_prepare) in order, each only if its count N exceeds
+ * 500 (masked rejection on 32-bit draws, exactly RandomState.randint).
  *   counts [B*I] int32  (out) set pixels per plane
  *   ranks  [B*I][500] int32 (out) row indices into pts[mask]; untouched when N <= 500
  * ------------------------------------------------------------------------- */
-int la3d_sample_ranks(const uint32_t* chunk_counts, int B, int I, int H, int W, uint32_t seed, uint32_t image_offset,
-                      int32_t* counts, int32_t* ranks, la3d_stream_t stream);
+int la3d_sample_ranks(const uint32_t* chunk_counts, const void* prep, int B, int I, int H, int W, int32_t* counts,
+                      int32_t* ranks, la3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Oriented box per (image, instance) from depth + scanned masks.  Replaces the
  * composition depth_to_points -> pts[mask] -> estimate_bbox -> project_to_2d
  * (src/util.py:52-75, src/util_3dbox.py:106-224, src/util.py:227-229,
  * src/tools/combine_results.py:238-246) without materialising the point cloud.
- *   depth [B][H][W] float; K [B][9] double intrinsics; ground nullable [B*I][3] double
- *   bits / chunk_counts / counts / ranks: outputs of the two calls above
+ *   depth [B][H][W] float; prep: output of la3d_fit_prepare (cameras, ground rotations)
+ *   bits / chunk_counts / ranks: outputs of la3d_mask_scan and la3d_sample_ranks
  *   records [B*I][64] float (rec_f64 = 0) or double (rec_f64 = 1)
  * ------------------------------------------------------------------------- */
-int la3d_fit_scanned(const float* depth, const double* K, const double* ground, const uint32_t* bits,
-                     const uint32_t* chunk_counts, const int32_t* counts, const int32_t* ranks, int B, int I, int H,
-                     int W, int method, int yaw_steps, void* records, int rec_f64, la3d_stream_t stream);
+int la3d_fit_scanned(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
+                     const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps, void* records,
+                     int rec_f64, la3d_stream_t stream);
 
-/* The three calls above as one pipeline.  `workspace` needs la3d_fit_workspace_bytes().
- * With the environment variable LA3D_PARTS=n (n > 1; experimental, off by default because it
- * measured slower on B200) the batch is cut into n parts: the scans of all parts run back to back
- * on `stream`, the sampler and fit kernel of a part run on an internal high-priority stream as
- * soon as that part is scanned, and `stream` waits for them before the call returns - to the
- * caller the call is still one asynchronous operation on `stream`, with identical results. */
+/* The four calls above as one pipeline of three launches on `stream`: the preparation rides in the
+ * mask scan's launch (B extra CTAs at the front of its grid, so the latency-bound seeding hides
+ * under the HBM-bound scan), then la3d_sample_ranks and la3d_fit_scanned.  `workspace` needs
+ * la3d_fit_workspace_bytes() bytes, 256-byte aligned. */
 size_t la3d_fit_workspace_bytes(int B, int I, int H, int W);
 int la3d_fit_boxes(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
                    int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed, uint32_t image_offset,
                    void* workspace, size_t workspace_bytes, void* records, int rec_f64, la3d_stream_t stream);
-
-/* Optional timing of the scans inside la3d_fit_boxes: after la3d_set_profiling(1), every call
- * brackets the mask scan of each part with timing events on `stream`; once the stream has been
- * synchronised, la3d_last_scan_ms() writes the per-part durations (ms) of the last call on this
- * device and returns how many parts there were (0 when the call ran unsplit), or a negative code. */
-void la3d_set_profiling(int on);
-int la3d_last_scan_ms(float* ms, int max_parts);
 
 /* ---------------------------------------------------------------------------
  * Oriented box from explicit point sets.  Replaces estimate_bbox,

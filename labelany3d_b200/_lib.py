@@ -20,14 +20,15 @@ SIGNATURES = {
     "la3d_chunks_per_plane": (_sz, [_i, _i]),
     "la3d_words_per_plane": (_sz, [_i, _i]),
     "la3d_mask_scan": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "la3d_sample_ranks": (_i, [_vp, _i, _i, _i, _i, _u32, _u32, _vp, _vp, _vp]),
-    "la3d_fit_scanned": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "la3d_prep_bytes": (_sz, [_i, _i]),
+    "la3d_fit_prepare": (_i, [_vp, _vp, _i, _i, _u32, _u32, _vp, _sz, _vp]),
+    "la3d_set_mt_blocks": (None, [_i]),
+    "la3d_sample_ranks": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "la3d_fit_scanned": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "la3d_fit_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "la3d_fit_boxes": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _i, _vp]),
     "la3d_fit_points": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "la3d_project_points": (_i, [_vp, _vp, _vp, C.c_longlong, _vp, _vp]),
-    "la3d_set_profiling": (None, [_i]),
-    "la3d_last_scan_ms": (_i, [_vp, _i]),
 }
 
 _lib = None

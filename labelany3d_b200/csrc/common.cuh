@@ -14,6 +14,8 @@ namespace la3d {
 constexpr int kChunkPx = 512;
 constexpr int kChunkWords = 16;
 
+constexpr int kMtN = 624;      // MT19937 state words
+
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t err, const char* what);
 
@@ -118,5 +120,58 @@ __device__ __forceinline__ void rigid_exact(const double* __restrict__ R, const 
     z = __dadd_rn(z, t[2]);
   }
 }
+
+// Rg of util_3dbox.py:128-134: Rodrigues rotation taking (0,-1,0) to the ground
+// normal, which is flipped first when dot((0,-1,0), g) <= 0.  0/0 -> NaN when the
+// two are parallel, exactly like the reference.  g == nullptr: identity.
+__device__ inline void ground_rotation(const double* g, double* Rg) {
+  if (!g) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rg[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  double g0 = g[0], g1 = g[1], g2 = g[2];
+  const double dotp = 0.0 * g0 + (-1.0) * g1 + 0.0 * g2;
+  if (dotp <= 0.0) { g0 = -g0; g1 = -g1; g2 = -g2; }
+  const double a0 = 0.0, a1 = -1.0, a2 = 0.0;
+  const double nb = sqrt(g0 * g0 + g1 * g1 + g2 * g2);
+  double b0 = g0, b1 = g1, b2 = g2;
+  if (nb != 0.0) { b0 = g0 / nb; b1 = g1 / nb; b2 = g2 / nb; }
+  const double ax = a1 * b2 - a2 * b1, ay = a2 * b0 - a0 * b2, az = a0 * b1 - a1 * b0;
+  const double cosang = a0 * b0 + a1 * b1 + a2 * b2;
+  const double S[9] = {0.0, -az, ay, az, 0.0, -ax, -ay, ax, 0.0};
+  const double nrm = sqrt(ax * ax + ay * ay + az * az);
+  const double nn = nrm * nrm;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double s2 = S[i * 3 + 0] * S[0 * 3 + j] + S[i * 3 + 1] * S[1 * 3 + j] + S[i * 3 + 2] * S[2 * 3 + j];
+      Rg[i * 3 + j] = ((i == j ? 1.0 : 0.0) + S[i * 3 + j]) + s2 * (1.0 - cosang) / nn;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// "prep" buffer of the scanned-mask path (la3d_fit_prepare): everything a batch
+// needs that does not depend on the masks - per image the intrinsics and their
+// inverse and the pre-generated MT19937 words (+ the state to continue from),
+// per box the ground rotation.
+// ---------------------------------------------------------------------------
+struct PrepCamera {
+  double K[9];
+  double Kinv[9];
+};
+struct PrepView {
+  PrepCamera* cams;   // [B]
+  double* Rg;         // [B*I][9]
+  uint32_t* state;    // [B][624] generator state after the pre-generated words
+  uint32_t* words;    // [B][nblk*624] tempered outputs
+  int nblk;
+  size_t bytes;
+};
+PrepView prep_view(void* base, int B, int I, int nblk);
+int prep_blocks(int I);
+int launch_sample(const uint32_t* chunk_counts, const PrepView& pv, int B, int I, int chunks, int32_t* counts,
+                  int32_t* ranks, cudaStream_t s);
 
 }  // namespace la3d

@@ -38,8 +38,9 @@ struct FitArgs {
   const float* depth;
   const uint32_t* bits;
   const uint32_t* chunk_counts;
-  const int32_t* counts;
   const int32_t* ranks;
+  const PrepCamera* cams;   // [images] intrinsics and their inverse (la3d_fit_prepare)
+  const double* Rg_pre;     // [boxes][9] ground rotations (la3d_fit_prepare)
   int I, HW, W, chunks;
   // explicit-point source
   const double* pts;
@@ -154,36 +155,6 @@ __device__ __forceinline__ int first_strict_min(const double* areas, int n, Smem
 #pragma unroll
   for (int w = 0; w < kWarps; ++w) r.offer(sm.red[w][0], sm.ired[w][0]);
   return r.idx;
-}
-
-// Rg of util_3dbox.py:128-134: Rodrigues rotation taking (0,-1,0) to the ground
-// normal, which is flipped first when dot((0,-1,0), g) <= 0.  0/0 -> NaN when the
-// two are parallel, exactly like the reference.
-__device__ void ground_rotation(const double* g, double* Rg) {
-  if (!g) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) Rg[i] = (i % 4 == 0) ? 1.0 : 0.0;
-    return;
-  }
-  double g0 = g[0], g1 = g[1], g2 = g[2];
-  const double dotp = 0.0 * g0 + (-1.0) * g1 + 0.0 * g2;
-  if (dotp <= 0.0) { g0 = -g0; g1 = -g1; g2 = -g2; }
-  const double a0 = 0.0, a1 = -1.0, a2 = 0.0;
-  const double nb = sqrt(g0 * g0 + g1 * g1 + g2 * g2);
-  double b0 = g0, b1 = g1, b2 = g2;
-  if (nb != 0.0) { b0 = g0 / nb; b1 = g1 / nb; b2 = g2 / nb; }
-  const double ax = a1 * b2 - a2 * b1, ay = a2 * b0 - a0 * b2, az = a0 * b1 - a1 * b0;
-  const double cosang = a0 * b0 + a1 * b1 + a2 * b2;
-  const double S[9] = {0.0, -az, ay, az, 0.0, -ax, -ay, ax, 0.0};
-  const double nrm = sqrt(ax * ax + ay * ay + az * az);
-  const double nn = nrm * nrm;
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const double s2 = S[i * 3 + 0] * S[0 * 3 + j] + S[i * 3 + 1] * S[1 * 3 + j] + S[i * 3 + 2] * S[2 * 3 + j];
-      Rg[i * 3 + j] = ((i == j ? 1.0 : 0.0) + S[i * 3 + j]) + s2 * (1.0 - cosang) / nn;
-    }
 }
 
 // ---- yaw estimators -----------------------------------------------------------------
@@ -399,13 +370,19 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int img = kScanned ? box / a.I : box;
 
-  // camera and ground rotation: one thread each, overlapped with the prefix build
-  if (tid == 0 && a.K) {
+  if (kScanned) {
+    // camera and ground rotation were prepared per image / per box (la3d_fit_prepare)
+    if (tid < 9) sm.Kmat[tid] = __ldg(&a.cams[img].K[tid]);
+    else if (tid < 18) sm.Kinv[tid - 9] = __ldg(&a.cams[img].Kinv[tid - 9]);
+    else if (tid < 27) sm.Rg[tid - 18] = __ldg(a.Rg_pre + (size_t)box * 9 + (tid - 18));
+  } else {
+    // explicit points: one thread each, overlapped with the loads below
+    if (tid == 0 && a.K) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) sm.Kmat[i] = a.K[(size_t)img * 9 + i];
-    if (kScanned) invert3x3(sm.Kmat, sm.Kinv);
+      for (int i = 0; i < 9; ++i) sm.Kmat[i] = a.K[(size_t)img * 9 + i];
+    }
+    if (tid == 32) ground_rotation(a.ground ? a.ground + (size_t)box * 3 : nullptr, sm.Rg);
   }
-  if (tid == 32) ground_rotation(a.ground ? a.ground + (size_t)box * 3 : nullptr, sm.Rg);
 
   long long n_src;
   const double* src_pts = nullptr;
@@ -642,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
     for (int i = 0; i < 3; ++i) rec[LA3D_O_VERT + tid * 3 + i] = v2[i];
     // project_to_2d (util.py:227-229)
     double uu = CUDART_NAN, vv = CUDART_NAN;
-    if (a.K) {
+    if (kScanned || a.K) {
       const double h0 = sm.Kmat[0] * v2[0] + sm.Kmat[1] * v2[1] + sm.Kmat[2] * v2[2];
       const double h1 = sm.Kmat[3] * v2[0] + sm.Kmat[4] * v2[1] + sm.Kmat[5] * v2[2];
       const double h2 = sm.Kmat[6] * v2[0] + sm.Kmat[7] * v2[1] + sm.Kmat[8] * v2[2];
@@ -717,19 +694,20 @@ int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s) {
 }  // namespace
 }  // namespace la3d
 
-extern "C" int la3d_fit_scanned(const float* depth, const double* K, const double* ground, const uint32_t* bits,
-                                const uint32_t* chunk_counts, const int32_t* counts, const int32_t* ranks, int B,
-                                int I, int H, int W, int method, int yaw_steps, void* records, int rec_f64,
-                                la3d_stream_t stream) {
+extern "C" int la3d_fit_scanned(const float* depth, const void* prep, const uint32_t* bits,
+                                const uint32_t* chunk_counts, const int32_t* ranks, int B, int I, int H, int W,
+                                int method, int yaw_steps, void* records, int rec_f64, la3d_stream_t stream) {
   using namespace la3d;
-  LA3D_REQUIRE(depth && K && bits && chunk_counts && counts && ranks && records, "null pointer");
+  LA3D_REQUIRE(depth && prep && bits && chunk_counts && ranks && records, "null pointer");
   LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
   LA3D_REQUIRE(method != LA3D_METHOD_SWEEP || (yaw_steps > 0 && yaw_steps <= 16384), "sweep needs 1 <= yaw_steps <= 16384");
+  const PrepView pv = prep_view(const_cast<void*>(prep), B, I, prep_blocks(I));
   FitArgs a{};
-  a.depth = depth; a.bits = bits; a.chunk_counts = chunk_counts; a.counts = counts; a.ranks = ranks;
+  a.depth = depth; a.bits = bits; a.chunk_counts = chunk_counts; a.ranks = ranks;
+  a.cams = pv.cams; a.Rg_pre = pv.Rg;
   a.I = I; a.HW = H * W; a.W = W; a.chunks = (int)la3d_chunks_per_plane(H, W);
-  a.K = K; a.ground = ground; a.method = method; a.yaw_steps = yaw_steps; a.records = records; a.rec_f64 = rec_f64;
+  a.method = method; a.yaw_steps = yaw_steps; a.records = records; a.rec_f64 = rec_f64;
   return launch_fit(true, a, B * I, static_cast<cudaStream_t>(stream));
 }
 

@@ -2,16 +2,22 @@
 // (src/util.py:52-75 of the reference).  HBM-bound: 4 B read + 12 B (float) or
 // 24 B (double) written per pixel.
 //
-// lift_prep_kernel + lift_tile_kernel (the fast path): the cameras of all images
+// lift_prep_kernel + lift_bulk_kernel (the fast path): the cameras of all images
 // (inverse intrinsics, optional rigid transform) are prepared once per launch by one
-// thread per image into a stream-ordered scratch buffer; the tile kernel then needs
-// no shared memory and no barrier: one CTA = 4096 consecutive pixels of one image,
-// each thread issues four 16-byte depth loads, reads its image's camera (uniform
-// loads) and writes 4 x 48 bytes.  One integer division per thread; the other pixel
-// coordinates advance incrementally.
+// thread per image into a stream-ordered scratch buffer.  One CTA of 128 threads then
+// owns a tile of 1536 (float) / 1024 (double) consecutive pixels of one image: each
+// thread issues its 16-byte depth loads, reads its image's camera (uniform loads),
+// converts, and writes its points into the CTA's shared-memory tile; one thread hands
+// the finished tile (18 / 24 KB, contiguous in the output) to the TMA unit with a
+// single cp.async.bulk shared -> global.  Measured on B200 (config 2 / config 4):
+// float 6.15 / 6.75 TB/s, double 6.46 / 6.70 TB/s = 0.94-1.03 of the measured copy peak.
+// lift_tile_kernel is the same without staging (direct 16-byte stores at a 48-byte
+// stride: 5.2 TB/s); kept selectable (LA3D_LIFT_VARIANT=0) for comparison.
 //
 // lift_scalar_kernel (generic fallback: pixel counts not divisible by 4, unaligned
 // buffers, no stream-ordered allocator): one pixel per thread, camera per CTA.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace la3d {
@@ -81,7 +87,8 @@ __device__ __forceinline__ void pixel_f32(float d, double ud, double vd, double 
   }
 }
 
-// 4 consecutive pixels starting at (v,u) of one image -> 48 bytes
+// 4 consecutive pixels starting at (v,u) of one image -> 48 bytes (kSmem: into the CTA's staging tile)
+template <bool kSmem>
 __device__ __forceinline__ void quad_f32(const float4 dq, int u, int v, int W, const Camera& cam,
                                          const Camera* __restrict__ full, const double* Rp, const double* tp,
                                          float* __restrict__ dst) {
@@ -103,12 +110,19 @@ __device__ __forceinline__ void quad_f32(const float4 dq, int u, int v, int W, c
     };
     one(dq.x, x0, y0, z0); one(dq.y, x1, y1, z1); one(dq.z, x2, y2, z2); one(dq.w, x3, y3, z3);
   }
-  st_stream(dst, x0, y0, z0, x1);
-  st_stream(dst + 4, y1, z1, x2, y2);
-  st_stream(dst + 8, z2, x3, y3, z3);
+  if (kSmem) {
+    reinterpret_cast<float4*>(dst)[0] = make_float4(x0, y0, z0, x1);
+    reinterpret_cast<float4*>(dst)[1] = make_float4(y1, z1, x2, y2);
+    reinterpret_cast<float4*>(dst)[2] = make_float4(z2, x3, y3, z3);
+  } else {
+    st_stream(dst, x0, y0, z0, x1);
+    st_stream(dst + 4, y1, z1, x2, y2);
+    st_stream(dst + 8, z2, x3, y3, z3);
+  }
 }
 
 // float64 result: the reference's operation order, bit for bit
+template <bool kSmem>
 __device__ __forceinline__ void quad_f64(const float4 dq, int u, int v, int W, const Camera& cam, const double* Rp,
                                          const double* tp, double* __restrict__ dst) {
   double x0, y0, z0, x1, y1, z1;
@@ -118,10 +132,14 @@ __device__ __forceinline__ void quad_f64(const float4 dq, int u, int v, int W, c
     rigid_exact(Rp, tp, x, y, z);
     if (++uu == W) { uu = 0; ++vv; }
   };
+  auto put = [&](double* p, double a, double b) {
+    if (kSmem) *reinterpret_cast<double2*>(p) = make_double2(a, b);
+    else st_stream(p, a, b);
+  };
   one(dq.x, x0, y0, z0); one(dq.y, x1, y1, z1);
-  st_stream(dst, x0, y0); st_stream(dst + 2, z0, x1); st_stream(dst + 4, y1, z1);
+  put(dst, x0, y0); put(dst + 2, z0, x1); put(dst + 4, y1, z1);
   one(dq.z, x0, y0, z0); one(dq.w, x1, y1, z1);
-  st_stream(dst + 6, x0, y0); st_stream(dst + 8, z0, x1); st_stream(dst + 10, y1, z1);
+  put(dst + 6, x0, y0); put(dst + 8, z0, x1); put(dst + 10, y1, z1);
 }
 
 // Cameras of all images, prepared once per launch by lift_prep_kernel.
@@ -167,12 +185,74 @@ __global__ void __launch_bounds__(kThreads, kMinCtas)
   for (int q = 0; q < kQuads; ++q) {
     if (px < HW) {
       const size_t o = ((size_t)b * HW + px) * 3;
-      if (kF64) quad_f64(dq[q], u, v, W, cam, Rp, tp, reinterpret_cast<double*>(out_) + o);
-      else quad_f32(dq[q], u, v, W, cam, gc, Rp, tp, reinterpret_cast<float*>(out_) + o);
+      if (kF64) quad_f64<false>(dq[q], u, v, W, cam, Rp, tp, reinterpret_cast<double*>(out_) + o);
+      else quad_f32<false>(dq[q], u, v, W, cam, gc, Rp, tp, reinterpret_cast<float*>(out_) + o);
     }
     px += kStepPx;
     u += du; v += dv;
     if (u >= W) { u -= W; ++v; }
+  }
+}
+
+// The bulk-store form of the tile kernel.  Direct stores of the tile kernel above write 16-byte
+// pieces at a 48-byte (float) / 96-byte (double) stride per lane, i.e. half sectors per
+// instruction.  Here the CTA assembles its tile of points in shared memory and ONE thread hands
+// the whole contiguous tile (up to 48 KB) to the TMA unit (cp.async.bulk shared -> global), which
+// writes full lines.  One CTA = kQuads x kT x 4 consecutive pixels of one image.
+template <bool kF64, int kQuads, int kT>
+__global__ void __launch_bounds__(kT)
+    lift_bulk_kernel(const float* __restrict__ depth, const Camera* __restrict__ cams, int has_R, int has_t, int HW,
+                     int W, int tiles_per_image, void* __restrict__ out_) {
+  extern __shared__ __align__(128) unsigned char stage_raw[];
+  constexpr int kStep = kT * 4;
+  constexpr int kTilePx = kQuads * kStep;
+  const int b = blockIdx.x / tiles_per_image;
+  const int tile = blockIdx.x - b * tiles_per_image;
+  const int px0 = tile * kTilePx;
+  int px = px0 + threadIdx.x * 4;
+  const float* img = depth + (size_t)b * HW;
+  float4 dq[kQuads];
+#pragma unroll
+  for (int q = 0; q < kQuads; ++q)
+    dq[q] = (px + q * kStep < HW) ? ld_stream(reinterpret_cast<const float4*>(img + px + q * kStep))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+  const Camera* gc = cams + b;
+  Camera cam;
+  if (kF64) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) cam.Kinv[i] = __ldg(&gc->Kinv[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) cam.M[i] = __ldg(&gc->M[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cam.t[i] = __ldg(&gc->t[i]);
+  }
+  const double* Rp = has_R ? gc->R : nullptr;
+  const double* tp = has_t ? gc->t : nullptr;
+  int v = px / W, u = px - v * W;
+  const int dv = kStep / W, du = kStep - dv * W;
+#pragma unroll
+  for (int q = 0; q < kQuads; ++q) {
+    if (px < HW) {
+      const size_t o = (size_t)(px - px0) * 3;
+      if (kF64) quad_f64<true>(dq[q], u, v, W, cam, Rp, tp, reinterpret_cast<double*>(stage_raw) + o);
+      else quad_f32<true>(dq[q], u, v, W, cam, gc, Rp, tp, reinterpret_cast<float*>(stage_raw) + o);
+    }
+    px += kStep;
+    u += du; v += dv;
+    if (u >= W) { u -= W; ++v; }
+  }
+  // generic-proxy writes -> visible to the async proxy, then one bulk store of the whole tile
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int n = min(kTilePx, HW - px0);
+    const uint32_t bytes = (uint32_t)n * 3u * (kF64 ? 8u : 4u);
+    unsigned char* dst = static_cast<unsigned char*>(out_) + ((size_t)b * HW + px0) * 3 * (kF64 ? 8 : 4);
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage_raw);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the tile must outlive the read
   }
 }
 
@@ -210,6 +290,23 @@ __global__ void __launch_bounds__(kThreads) lift_scalar_kernel(const float* __re
   }
 }
 
+template <bool kF64, int kQ, int kT>
+int launch_bulk(const float* depth, const Camera* cams, const double* R, const double* t, int B, int HW, int W,
+                void* out, cudaStream_t s) {
+  constexpr int kTilePx = kQ * kT * 4;
+  constexpr int kSmem = kTilePx * 3 * (kF64 ? 8 : 4);
+  const int tiles = (HW + kTilePx - 1) / kTilePx;
+  LA3D_REQUIRE((long long)tiles * B < (1ll << 31), "grid too large");
+  static_assert(kSmem <= 48 * 1024, "tile must fit the default dynamic shared memory limit");
+  lift_bulk_kernel<kF64, kQ, kT><<<(unsigned)(tiles * B), kT, kSmem, s>>>(depth, cams, R != nullptr, t != nullptr, HW, W, tiles, out);
+  return LA3D_OK;
+}
+
+int lift_variant() {
+  static const int v = getenv("LA3D_LIFT_VARIANT") ? atoi(getenv("LA3D_LIFT_VARIANT")) : 1;   // 0: direct stores (no staging)
+  return v;
+}
+
 constexpr int kQuads = 4;      // 16-byte loads in flight per thread
 constexpr int kMinCtas = 3;    // resident CTAs per SM the tile kernels are compiled for
 
@@ -237,10 +334,22 @@ extern "C" int la3d_depth_lift(const float* depth, const double* K, int k_stride
     const int tiles = (HW + kQuads * kStepPx - 1) / (kQuads * kStepPx);
     LA3D_REQUIRE((long long)tiles * B < (1ll << 31), "grid too large");
     const unsigned grid = (unsigned)(tiles * B);
-    if (out_f64)
-      lift_tile_kernel<true, kQuads, kMinCtas><<<grid, kThreads, 0, s>>>(depth, cams, R != nullptr, t != nullptr, HW, W, tiles, out);
-    else
-      lift_tile_kernel<false, kQuads, kMinCtas><<<grid, kThreads, 0, s>>>(depth, cams, R != nullptr, t != nullptr, HW, W, tiles, out);
+    const int variant = lift_variant();
+    if (variant == 0) {
+      if (out_f64)
+        lift_tile_kernel<true, kQuads, kMinCtas><<<grid, kThreads, 0, s>>>(depth, cams, R != nullptr, t != nullptr, HW, W, tiles, out);
+      else
+        lift_tile_kernel<false, kQuads, kMinCtas><<<grid, kThreads, 0, s>>>(depth, cams, R != nullptr, t != nullptr, HW, W, tiles, out);
+    } else {
+      int rc = LA3D_OK;
+      // tile sizes measured on B200 (tools/lift_variants.py): 1536-pixel tiles (18 KB) for float,
+      // 1024-pixel tiles (24 KB) for double; variant 2 = 2048-pixel tiles for both
+      if (variant == 2) rc = out_f64 ? launch_bulk<true, 4, 128>(depth, cams, R, t, B, HW, W, out, s)
+                                     : launch_bulk<false, 4, 128>(depth, cams, R, t, B, HW, W, out, s);
+      else rc = out_f64 ? launch_bulk<true, 2, 128>(depth, cams, R, t, B, HW, W, out, s)
+                        : launch_bulk<false, 3, 128>(depth, cams, R, t, B, HW, W, out, s);
+      if (rc) return rc;
+    }
     LA3D_CUDA(cudaGetLastError());
     LA3D_CUDA(cudaFreeAsync(cams, s));
   } else {

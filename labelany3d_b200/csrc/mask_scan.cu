@@ -9,7 +9,11 @@
 //
 // A warp converts 4 consecutive 512-pixel chunks per step: 4 independent
 // 16-byte loads per lane are in flight before the first is used.
-#include "common.cuh"
+//
+// kPrep: the first `B` CTAs of the launch do not scan; they run the batch's
+// mask-independent, latency-bound preparation (MT19937 words, cameras, ground rotations;
+// prep.cuh), which so hides under the HBM-bound scan without a second stream.
+#include "prep.cuh"
 
 namespace la3d {
 namespace {
@@ -51,13 +55,17 @@ __device__ __forceinline__ uint32_t pack16(uint4 q) {
   return acc;
 }
 
-template <bool k01, bool kVec>
-__global__ void __launch_bounds__(kThreads) mask_scan_kernel(const uint8_t* __restrict__ masks, int HW,
-                                                             int chunks_per_plane, int tiles_per_plane,
-                                                             uint32_t* __restrict__ bits,
-                                                             uint32_t* __restrict__ chunk_counts) {
-  const int plane = blockIdx.x / tiles_per_plane;
-  const int tile = blockIdx.x - plane * tiles_per_plane;
+template <bool k01, bool kVec, bool kPrep>
+__global__ void __launch_bounds__(kThreads, kPrep ? 8 : 1)
+    mask_scan_kernel(const uint8_t* __restrict__ masks, int HW, int chunks_per_plane, int tiles_per_plane,
+                     uint32_t* __restrict__ bits, uint32_t* __restrict__ chunk_counts, PrepArgs pa) {
+  int bid = blockIdx.x;
+  if (kPrep) {
+    if (bid < pa.B) { prep_body<kThreads>(pa, bid); return; }     // CTA-uniform
+    bid -= pa.B;
+  }
+  const int plane = bid / tiles_per_plane;
+  const int tile = bid - plane * tiles_per_plane;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = tile * kTileChunks + warp * kUnroll;
   const uint8_t* src = masks + (size_t)plane * HW;
@@ -100,23 +108,35 @@ extern "C" size_t la3d_chunks_per_plane(int H, int W) {
 }
 extern "C" size_t la3d_words_per_plane(int H, int W) { return la3d_chunks_per_plane(H, W) * la3d::kChunkWords; }
 
-extern "C" int la3d_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
-                              uint32_t* chunk_counts, la3d_stream_t stream) {
-  using namespace la3d;
+namespace la3d {
+// prep == nullptr: the plain scan.  Otherwise prep->B extra CTAs at the front of the grid prepare the batch.
+int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
+                     uint32_t* chunk_counts, const PrepArgs* prep, cudaStream_t s) {
   LA3D_REQUIRE(masks && bits && chunk_counts, "null pointer");
   LA3D_REQUIRE(planes > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
   const int HW = H * W;
   const int chunks = (int)la3d_chunks_per_plane(H, W);
   const int tiles = (chunks + kTileChunks - 1) / kTileChunks;
-  LA3D_REQUIRE((long long)tiles * planes < (1ll << 31), "grid too large");
+  const long long ctas = (long long)tiles * planes + (prep ? prep->B : 0);
+  LA3D_REQUIRE(ctas < (1ll << 31), "grid too large");
   const bool vec = (HW % 16 == 0) && aligned16(masks);
-  dim3 grid((unsigned)(tiles * planes)), block(kThreads);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define LAUNCH(B01, VEC) mask_scan_kernel<B01, VEC><<<grid, block, 0, s>>>(masks, HW, chunks, tiles, bits, chunk_counts)
-  if (mask_is_01) { if (vec) LAUNCH(true, true); else LAUNCH(true, false); }
-  else            { if (vec) LAUNCH(false, true); else LAUNCH(false, false); }
+  dim3 grid((unsigned)ctas), block(kThreads);
+  const PrepArgs pa = prep ? *prep : PrepArgs{};
+#define LAUNCH(B01, VEC, PREP) \
+  mask_scan_kernel<B01, VEC, PREP><<<grid, block, 0, s>>>(masks, HW, chunks, tiles, bits, chunk_counts, pa)
+#define LAUNCH2(B01, VEC) do { if (prep) LAUNCH(B01, VEC, true); else LAUNCH(B01, VEC, false); } while (0)
+  if (mask_is_01) { if (vec) LAUNCH2(true, true); else LAUNCH2(true, false); }
+  else            { if (vec) LAUNCH2(false, true); else LAUNCH2(false, false); }
+#undef LAUNCH2
 #undef LAUNCH
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
+}
+}  // namespace la3d
+
+extern "C" int la3d_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
+                              uint32_t* chunk_counts, la3d_stream_t stream) {
+  return la3d::launch_mask_scan(masks, planes, H, W, mask_is_01, bits, chunk_counts, nullptr,
+                                static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,108 @@
+// MT19937 block generation and the mask-independent preparation of a batch (see sample.cu).
+// Shared by the stand-alone prep kernel (sample.cu) and by the prep CTAs that ride in the mask
+// scan's launch (mask_scan.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace la3d {
+
+constexpr int kMtM = 397;
+
+struct PrepArgs {
+  const double* K;        // [B][9]
+  const double* ground;   // [B*I][3] or null
+  int B, I;
+  uint32_t seed0;         // image b seeds with seed0 + b (mod 2^32)
+  PrepView pv;
+};
+
+__device__ __forceinline__ uint32_t twist(uint32_t cur, uint32_t nxt) {
+  uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+  return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__device__ __forceinline__ uint32_t temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+// Next 624 words.  Word kk needs old[kk], old[kk+1] and old[kk+397] (kk < 227) or NEW[kk-227]:
+// three phases [0,227), [227,454), [454,623] each read only words no thread of the phase writes,
+// except old[kk+1] at the seam, so every phase reads, synchronises, then writes.  The tempered
+// words go to `out` (shared or global); the caller synchronises before reading them.
+template <int kT>
+__device__ __forceinline__ void mt_next_block(uint32_t* mt, uint32_t* out) {
+  const int tid = threadIdx.x;
+  constexpr int kSpan = kMtN - kMtM;                 // 227
+  constexpr int kIter = (kSpan + kT - 1) / kT;
+#pragma unroll
+  for (int phase = 0; phase < 3; ++phase) {
+    const int lo = phase * kSpan, hi = min(lo + kSpan, kMtN - 1);
+    uint32_t val[kIter];
+#pragma unroll
+    for (int j = 0; j < kIter; ++j) {
+      const int kk = lo + tid + j * kT;
+      val[j] = 0;
+      if (kk < hi) {
+        const uint32_t far = (kk < kSpan) ? mt[kk + kMtM] : mt[kk - kSpan];
+        val[j] = far ^ twist(mt[kk], mt[kk + 1]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kIter; ++j) {
+      const int kk = lo + tid + j * kT;
+      if (kk < hi) mt[kk] = val[j];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) mt[kMtN - 1] = mt[kMtM - 1] ^ twist(mt[kMtN - 1], mt[0]);
+  __syncthreads();
+  for (int k = tid; k < kMtN; k += kT) out[k] = temper(mt[k]);
+}
+
+// One CTA of kT threads prepares image b: thread 0 seeds MT19937 (init_genrand) while thread 32
+// inverts the intrinsics and threads 64.. build the ground rotations; then the whole CTA
+// generates the image's first pv.nblk blocks of tempered words and saves the state.
+template <int kT>
+__device__ __forceinline__ void prep_body(const PrepArgs& pa, int b) {
+  __shared__ uint32_t mt[kMtN];
+  const int tid = threadIdx.x;
+  const PrepView& pv = pa.pv;
+  if (tid == 0) {
+    uint32_t s = pa.seed0 + (uint32_t)b;       // mod 2^32, as np.random.seed requires
+#pragma unroll 8
+    for (int i = 0; i < kMtN; ++i) {
+      mt[i] = s;
+      s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
+    }
+  } else if (tid == 32) {
+    PrepCamera* cam = pv.cams + b;
+    double Km[9], Kinv[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Km[i] = pa.K[(size_t)b * 9 + i];
+    invert3x3(Km, Kinv);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { cam->K[i] = Km[i]; cam->Kinv[i] = Kinv[i]; }
+  } else if (tid >= 64) {
+    for (int i = tid - 64; i < pa.I; i += kT - 64) {
+      double Rg[9];
+      ground_rotation(pa.ground ? pa.ground + ((size_t)b * pa.I + i) * 3 : nullptr, Rg);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) pv.Rg[((size_t)b * pa.I + i) * 9 + k] = Rg[k];
+    }
+  }
+  __syncthreads();
+  uint32_t* words = pv.words + (size_t)b * pv.nblk * kMtN;
+  for (int blk = 0; blk < pv.nblk; ++blk) mt_next_block<kT>(mt, words + (size_t)blk * kMtN);
+  for (int k = tid; k < kMtN; k += kT) pv.state[(size_t)b * kMtN + k] = mt[k];
+}
+
+int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
+                     uint32_t* chunk_counts, const PrepArgs* prep, cudaStream_t s);
+
+}  // namespace la3d

@@ -110,28 +110,69 @@ def mask_scan(masks):
     return bits, cc
 
 
-def sample_ranks(chunk_counts, B, I, H, W, seed=0, image_offset=0):
+def fit_prepare(K, ground, B, I, seed=0, image_offset=0):
+    """Mask-independent preparation of a batch (``la3d_fit_prepare``): per-image MT19937 words,
+    intrinsics and their inverse, per-box ground rotations.  Returns the opaque ``prep`` buffer
+    (uint8 CUDA tensor) that :func:`sample_ranks` and :func:`fit_scanned` consume."""
+    lib = _lib.load()
+    K = _need_cuda("K", K, torch.float64)
+    if tuple(K.shape) != (B, 3, 3):
+        raise ValueError(f"K must be [{B},3,3]")
+    if ground is not None:
+        ground = _need_cuda("ground", ground, torch.float64)
+        if tuple(ground.shape) != (B, I, 3):
+            raise ValueError(f"ground must be [{B},{I},3]")
+    nbytes = int(lib.la3d_prep_bytes(B, I))
+    prep = torch.empty(nbytes, dtype=torch.uint8, device=K.device)
+    with torch.cuda.device(K.device):
+        rc = lib.la3d_fit_prepare(_ptr(K), _ptr(ground), B, I, int(seed) & 0xFFFFFFFF, int(image_offset) & 0xFFFFFFFF,
+                                  _ptr(prep), nbytes, _stream())
+    _lib.check(rc, "la3d_fit_prepare")
+    return prep
+
+
+def sample_ranks(chunk_counts, B, I, H, W, seed=0, image_offset=0, prep=None):
     """Per-plane pixel counts and the reference's 500 random rows of ``pts[mask]``.
 
     Returns ``(counts[B,I] int32, ranks[B,I,500] int32)``; ``ranks`` of planes with at
-    most 500 pixels are left at -1 (the reference keeps all their points).
+    most 500 pixels are left at -1 (the reference keeps all their points).  ``prep``: the
+    buffer of :func:`fit_prepare` (made here, with identity cameras, when not given).
     """
     lib = _lib.load()
     cc = _need_cuda("chunk_counts", chunk_counts, torch.int32)
+    if prep is None:
+        eye = torch.eye(3, dtype=torch.float64, device=cc.device).expand(B, 3, 3).contiguous()
+        prep = fit_prepare(eye, None, B, I, seed, image_offset)
     counts = torch.empty((B, I), dtype=torch.int32, device=cc.device)
     ranks = torch.full((B, I, SUBSAMPLE), -1, dtype=torch.int32, device=cc.device)
     with torch.cuda.device(cc.device):
-        rc = lib.la3d_sample_ranks(_ptr(cc), B, I, H, W, int(seed) & 0xFFFFFFFF, int(image_offset) & 0xFFFFFFFF,
-                                   _ptr(counts), _ptr(ranks), _stream())
+        rc = lib.la3d_sample_ranks(_ptr(cc), _ptr(prep), B, I, H, W, _ptr(counts), _ptr(ranks), _stream())
     _lib.check(rc, "la3d_sample_ranks")
     return counts, ranks
+
+
+def fit_scanned(depth, prep, bits, chunk_counts, ranks, method="pca", yaw_steps=0, out_dtype=torch.float64):
+    """The fit kernel alone (``la3d_fit_scanned``) on the outputs of :func:`mask_scan`,
+    :func:`fit_prepare` and :func:`sample_ranks`; returns ``records[B,I,64]``."""
+    lib = _lib.load()
+    depth = _need_cuda("depth", depth, torch.float32)
+    B, H, W = depth.shape
+    I = ranks.shape[1]
+    rec = torch.empty((B, I, REC), dtype=out_dtype, device=depth.device)
+    with torch.cuda.device(depth.device):
+        rc = lib.la3d_fit_scanned(_ptr(depth), _ptr(prep), _ptr(bits), _ptr(chunk_counts), _ptr(ranks), B, I, H, W,
+                                  _method_id(method), int(yaw_steps), _ptr(rec), int(out_dtype == torch.float64),
+                                  _stream())
+    _lib.check(rc, "la3d_fit_scanned")
+    return rec
 
 
 class BoxFitter:
     """Reusable plan for ``fit_boxes`` on a fixed shape: owns the workspace and the output.
 
-    One call = three kernels on the current stream (mask scan, subsample ranks, fit);
-    nothing is allocated and nothing synchronises.
+    One call = three launches on the current stream (mask scan with the mask-independent
+    preparation riding in its grid, subsample ranks, fit); nothing is allocated and nothing
+    synchronises.
     """
 
     def __init__(self, B, I, H, W, device="cuda", out_dtype=torch.float64):
@@ -149,8 +190,10 @@ class BoxFitter:
     def __call__(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0, out=None,
                  events=None):
         """Fit every (image, instance) box; returns ``records[B,I,64]`` (a buffer owned by the plan
-        unless ``out`` is given).  ``events``: optional list of 4 ``torch.cuda.Event`` recorded before
-        the scan, between the kernels and after the fit (per-kernel timing without a profiler)."""
+        unless ``out`` is given).  ``events``: optional list of 5 ``torch.cuda.Event``; the four kernels
+        are then issued one after the other on the current stream (no overlap) with the events
+        recorded before, between and after them: prepare, scan, sample, fit (per-kernel timing
+        without a profiler)."""
         B, I, H, W = self.shape
         depth = _need_cuda("depth", depth, torch.float32)
         K = _need_cuda("K", K, torch.float64)
@@ -177,17 +220,19 @@ class BoxFitter:
                                         _ptr(rec), f64, st)
                 _lib.check(rc, "la3d_fit_boxes")
             else:
-                # the same three kernels through the step-wise entry points, with events in between
-                bits, cc, counts, ranks = self._carve()
+                # the same kernels through the step-wise entry points, serialised, with events in between
+                bits, cc, counts, ranks, prep, prep_bytes = self._carve()
+                sd, off = int(seed) & 0xFFFFFFFF, int(image_offset) & 0xFFFFFFFF
                 events[0].record()
-                _lib.check(lib.la3d_mask_scan(_ptr(m8), B * I, H, W, is01, bits, cc, st), "la3d_mask_scan")
+                _lib.check(lib.la3d_fit_prepare(_ptr(K), _ptr(ground), B, I, sd, off, prep, prep_bytes, st), "la3d_fit_prepare")
                 events[1].record()
-                _lib.check(lib.la3d_sample_ranks(cc, B, I, H, W, int(seed) & 0xFFFFFFFF,
-                                                 int(image_offset) & 0xFFFFFFFF, counts, ranks, st), "la3d_sample_ranks")
+                _lib.check(lib.la3d_mask_scan(_ptr(m8), B * I, H, W, is01, bits, cc, st), "la3d_mask_scan")
                 events[2].record()
-                _lib.check(lib.la3d_fit_scanned(_ptr(depth), _ptr(K), _ptr(ground), bits, cc, counts, ranks, B, I, H, W,
-                                                _method_id(method), int(yaw_steps), _ptr(rec), f64, st), "la3d_fit_scanned")
+                _lib.check(lib.la3d_sample_ranks(cc, prep, B, I, H, W, counts, ranks, st), "la3d_sample_ranks")
                 events[3].record()
+                _lib.check(lib.la3d_fit_scanned(_ptr(depth), prep, bits, cc, ranks, B, I, H, W, _method_id(method),
+                                                int(yaw_steps), _ptr(rec), f64, st), "la3d_fit_scanned")
+                events[4].record()
         return rec
 
     def capture(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0, out=None):
@@ -220,8 +265,10 @@ class BoxFitter:
         o_cc = up(planes * words * 4)
         o_counts = up(o_cc + planes * chunks * 4)
         o_ranks = up(o_counts + planes * 4)
-        assert up(up(o_ranks + planes * SUBSAMPLE * 4) + B * 624 * 4) == self.ws_bytes
-        return base, base + o_cc, base + o_counts, base + o_ranks
+        o_prep = up(o_ranks + planes * SUBSAMPLE * 4)
+        prep_bytes = int(self.lib.la3d_prep_bytes(B, I))
+        assert up(o_prep + prep_bytes) == self.ws_bytes
+        return base, base + o_cc, base + o_counts, base + o_ranks, base + o_prep, prep_bytes
 
 
 def fit_boxes(depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0,

@@ -144,6 +144,46 @@ def test_legacy_randint_stream(ops, golden):
     np.testing.assert_array_equal(r.cpu().numpy()[0, 0], np.random.RandomState(2).randint(0, 2048, 500))
 
 
+def test_sampler_continues_when_pregenerated_words_run_out(ops):
+    """The words pre-generated under the scan are a budget, not a limit: with one 624-word block per
+    image (an instance needs 500-1000 draws) the sampler continues the generator from the saved state
+    and the ranks stay bit-identical to NumPy's stream and to the automatic budget."""
+    from labelany3d_b200 import _lib, synth
+    lib = _lib.load()
+    H, W = 96, 128
+    chunks, _ = ops.scan_layout(H, W)
+    rng = np.random.RandomState(5)
+    ns = rng.randint(501, H * W, size=(3, 6))
+    ns[1, 2] = 17                                              # no draw for this one
+    ns[2, 0] = 4097                                            # acceptance just above 1/2
+    cc = np.zeros((3, 6, chunks, 4), dtype=np.uint8)
+    for b in range(3):
+        for i in range(6):
+            full, rest = divmod(int(ns[b, i]), 128)
+            cc[b, i].reshape(-1)[:full] = 128
+            if rest:
+                cc[b, i].reshape(-1)[full] = rest
+    cc_dev = dev(cc.view(np.int32).reshape(18, chunks))
+    want = np.full((3, 6, 500), -1, dtype=np.int32)
+    for b in range(3):
+        rs = np.random.RandomState(77 + b)
+        for i in range(6):
+            if ns[b, i] > 500:
+                want[b, i] = rs.randint(0, ns[b, i], 500)
+    try:
+        for blocks in (1, 2, 0):
+            lib.la3d_set_mt_blocks(blocks)
+            counts, ranks = ops.sample_ranks(cc_dev, 3, 6, H, W, seed=70, image_offset=7)
+            np.testing.assert_array_equal(counts.cpu().numpy(), ns)
+            np.testing.assert_array_equal(ranks.cpu().numpy(), want)
+        depth, K, masks, ground = synth.make_inputs(2, H, W, 5, seed=9, device="cuda", area=(0.05, 0.3))
+        full = ops.fit_boxes(depth, K, masks, ground, "pca", seed=3).cpu().numpy()
+        lib.la3d_set_mt_blocks(1)
+        np.testing.assert_array_equal(ops.fit_boxes(depth, K, masks, ground, "pca", seed=3).cpu().numpy(), full)
+    finally:
+        lib.la3d_set_mt_blocks(0)
+
+
 # ------------------------------------------------------------------ a3-a8 box from explicit points
 def check_record(rec, ref, tol, skip=(orc.O_YAW, orc.O_NVALID)):
     """Per box: |diff| <= tol * max(1, largest finite magnitude in the reference record)."""

@@ -57,12 +57,15 @@ def main():
         out[f"scan{is01}_ms"] = med; out[f"scan{is01}_GBs"] = px * I / med / 1e6; out[f"scan{is01}_best_GBs"] = px * I / best / 1e6
     counts = torch.empty((B, I), dtype=torch.int32, device="cuda")
     ranks = torch.empty((B, I, 500), dtype=torch.int32, device="cuda")
-    med, best = timeit(lambda: lib.la3d_sample_ranks(cc.data_ptr(), B, I, H, W, 1234, 0, counts.data_ptr(), ranks.data_ptr(), st))
+    prep = torch.empty(lib.la3d_prep_bytes(B, I), dtype=torch.uint8, device="cuda")
+    med, best = timeit(lambda: lib.la3d_fit_prepare(K.data_ptr(), ground.data_ptr(), B, I, 1234, 0, prep.data_ptr(), prep.numel(), st))
+    out["prepare_ms"] = med
+    med, best = timeit(lambda: lib.la3d_sample_ranks(cc.data_ptr(), prep.data_ptr(), B, I, H, W, counts.data_ptr(), ranks.data_ptr(), st))
     out["sample_ms"] = med
     rec = torch.empty((B, I, 64), dtype=torch.float64, device="cuda")
     for name, mid, steps in (("pca", 0, 0), ("hull", 1, 0), ("sweep36", 2, 36), ("sweep360", 2, 360)):
-        med, best = timeit(lambda: lib.la3d_fit_scanned(depth.data_ptr(), K.data_ptr(), ground.data_ptr(), bits.data_ptr(), cc.data_ptr(),
-                                                        counts.data_ptr(), ranks.data_ptr(), B, I, H, W, mid, steps, rec.data_ptr(), 1, st))
+        med, best = timeit(lambda: lib.la3d_fit_scanned(depth.data_ptr(), prep.data_ptr(), bits.data_ptr(), cc.data_ptr(),
+                                                        ranks.data_ptr(), B, I, H, W, mid, steps, rec.data_ptr(), 1, st))
         out[f"fit_{name}_ms"] = med
     fit = ops.BoxFitter(B, I, H, W)
     for name, steps in (("pca", 0), ("sweep", c["yaw_steps"] or 36)):

@@ -24,15 +24,17 @@ counts = torch.empty((B, I), dtype=torch.int32, device="cuda")
 ranks = torch.empty((B, I, 500), dtype=torch.int32, device="cuda")
 rec = torch.empty((B, I, 64), dtype=torch.float64, device="cuda")
 o32 = torch.empty((B, H, W, 3), dtype=torch.float32, device="cuda")
+prep = torch.empty(lib.la3d_prep_bytes(B, I), dtype=torch.uint8, device="cuda")
 torch.cuda.synchronize()
 for _ in range(2):
     if "lift" in which:
         lib.la3d_depth_lift(depth.data_ptr(), K.data_ptr(), 9, 0, None, None, B, H, W, o32.data_ptr(), 0, st)
+    lib.la3d_fit_prepare(K.data_ptr(), ground.data_ptr(), B, I, 1234, 0, prep.data_ptr(), prep.numel(), st)
     lib.la3d_mask_scan(m8.data_ptr(), B * I, H, W, 1, bits.data_ptr(), cc.data_ptr(), st)
-    lib.la3d_sample_ranks(cc.data_ptr(), B, I, H, W, 1234, 0, counts.data_ptr(), ranks.data_ptr(), st)
+    lib.la3d_sample_ranks(cc.data_ptr(), prep.data_ptr(), B, I, H, W, counts.data_ptr(), ranks.data_ptr(), st)
     for name, mid, steps in (("pca", 0, 0), ("sweep", 2, c["yaw_steps"] or 36), ("hull", 1, 0)):
         if name in which:
-            lib.la3d_fit_scanned(depth.data_ptr(), K.data_ptr(), ground.data_ptr(), bits.data_ptr(), cc.data_ptr(),
-                                 counts.data_ptr(), ranks.data_ptr(), B, I, H, W, mid, steps, rec.data_ptr(), 1, st)
+            lib.la3d_fit_scanned(depth.data_ptr(), prep.data_ptr(), bits.data_ptr(), cc.data_ptr(),
+                                 ranks.data_ptr(), B, I, H, W, mid, steps, rec.data_ptr(), 1, st)
 torch.cuda.synchronize()
 print("done")
