@@ -331,3 +331,46 @@ def test_full_size_properties(ops):
     want = orc.fit_boxes(depth[sl].cpu().numpy(), K[sl].cpu().numpy(), masks[sl].cpu().numpy(),
                          ground[sl].cpu().numpy(), "sweep", 36, seed=1234, image_offset=3, impl="closed")
     check_record(r[sl], want, TOL_F64, skip=(orc.O_NVALID,))
+
+
+@pytest.mark.parametrize("cfg", [3, 4, 5])
+def test_full_size_other_configs(ops, cfg):
+    """BASELINE configs 3-5 at their full per-GPU size (config 3: 2048/8 images x 10 instances, pca;
+    config 4: 128 images of 1536x1536 x 20 instances, pca; config 5: 1024/8 images x 32 instances,
+    360-step sweep), through size-independent properties plus an oracle spot check."""
+    from labelany3d_b200 import synth
+    c = synth.CONFIGS[cfg]
+    B, I, H, W = c["B"] // c["gpus"], c["I"], c["H"], c["W"]
+    method, steps = c["method"], c["yaw_steps"]
+    depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=1234 + cfg, device="cuda", chunk=4 if cfg == 4 else 16)
+    fit = ops.BoxFitter(B, I, H, W)
+    r = fit(depth, K, masks, ground, method, steps, seed=1234).cpu().numpy()
+    # integer work, exact, by an independent route (torch reduction)
+    np.testing.assert_array_equal(r[..., orc.O_NMASK], masks.flatten(2).sum(-1).cpu().numpy())
+    assert (r[..., orc.O_STATUS] == 0).all() and (r[..., orc.O_NVALID] == 500).all()
+    Rc = r[..., orc.O_RCAM:orc.O_RCAM + 9].reshape(B, I, 3, 3)
+    np.testing.assert_allclose(Rc @ Rc.transpose(0, 1, 3, 2), np.broadcast_to(np.eye(3), Rc.shape), atol=1e-12)
+    assert (r[..., orc.O_DIM:orc.O_DIM + 3] >= 0).all()
+    # the reprojected corners are K @ vertex, and the 2D box bounds them
+    V = r[..., :24].reshape(B, I, 8, 3)
+    Kn = K.cpu().numpy()
+    h = np.einsum("bij,bnkj->bnki", Kn, V)
+    uv = h[..., :2] / h[..., 2:3]
+    np.testing.assert_allclose(r[..., orc.O_UV:orc.O_UV + 16].reshape(B, I, 8, 2), uv, rtol=1e-12, atol=1e-9)
+    np.testing.assert_array_equal(r[..., orc.O_BOX2D:orc.O_BOX2D + 2], r[..., orc.O_UV:orc.O_UV + 16].reshape(B, I, 8, 2).min(2))
+    np.testing.assert_array_equal(r[..., orc.O_BOX2D + 2:orc.O_BOX2D + 4], r[..., orc.O_UV:orc.O_UV + 16].reshape(B, I, 8, 2).max(2))
+    if method == "sweep":
+        # the chosen yaw is one of the candidates k * (pi/2) / K
+        k = r[..., orc.O_YAW] / (np.pi / 2) * steps
+        np.testing.assert_allclose(k, np.round(k), atol=1e-9)
+    # sharding independence and idempotence
+    h0 = B // 2
+    half = ops.BoxFitter(B - h0, I, H, W)
+    r2 = half(depth[h0:], K[h0:], masks[h0:], ground[h0:], method, steps, seed=1234, image_offset=h0).cpu().numpy()
+    np.testing.assert_array_equal(r2, r[h0:])
+    np.testing.assert_array_equal(fit(depth, K, masks, ground, method, steps, seed=1234).cpu().numpy(), r)
+    # one image against the oracle at full resolution
+    sl = slice(B - 1, B)
+    want = orc.fit_boxes(depth[sl].cpu().numpy(), K[sl].cpu().numpy(), masks[sl].cpu().numpy(),
+                         ground[sl].cpu().numpy(), method, steps, seed=1234, image_offset=B - 1, impl="closed")
+    check_record(r[sl], want, TOL_F64 * (10 if method == "pca" else 1), skip=(orc.O_NVALID,))
