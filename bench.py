@@ -48,16 +48,21 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=256, help="images of the workload the CPU baseline is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: records written into every rank's gathered buffer by the fit kernel over peer memory "
+                         "(p2p) or one NCCL all-gather after the fit (nccl)")
     return ap.parse_args()
 
 
-def config_dict(n_gpus):
+def config_dict(n_gpus, collective="p2p"):
     w = WORKLOAD
+    how = {"p2p": ", records written by the fit kernel into every rank's gathered buffer over NVLink peer memory + flag barrier, each step",
+           "nccl": ", NCCL all-gather of the packed records each step"}[collective]
     return {"workload": f"BASELINE configs[1]: batch={w['B']} images/GPU, {w['W']}x{w['H']} depth, {w['I']} instances/image, "
                         f"{w['yaw_steps']}-step yaw sweep",
             "images_per_gpu": w["B"], "global_images": w["B"] * n_gpus, "instances_per_image": w["I"],
             "height": w["H"], "width": w["W"], "method": w["method"], "yaw_steps": w["yaw_steps"], "subsample": 500,
-            "parallelism": f"images sharded over {n_gpus} GPU(s)" + (", all-gather of packed records each step" if n_gpus > 1 else ""),
+            "parallelism": f"images sharded over {n_gpus} GPU(s)" + (how if n_gpus > 1 else ""),
             "l2": "inputs (944 MB/GPU/step) exceed the 126 MB L2; no flush needed"}
 
 
@@ -219,14 +224,16 @@ def main():
     B, I, H, W = w["B"], w["I"], w["H"], w["W"]
     # every rank owns B images of a B*world batch; inputs are generated where they live
     depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=SEED + 1000 * rank, device=dev)
-    fitter = la_dist.ShardedBoxFitter(B * world, I, H, W, device=dev, out_dtype=torch.float32) if world > 1 else None
+    fitter = (la_dist.ShardedBoxFitter(B * world, I, H, W, device=dev, out_dtype=torch.float32, collective=args.collective)
+              if world > 1 else None)
     single = ops.BoxFitter(B, I, H, W, device=dev, out_dtype=torch.float32)
     boxes_per_step = B * I * world
 
     def step(events=None):
-        if fitter is not None:
-            return fitter(depth, K, masks, ground, w["method"], w["yaw_steps"], seed=1234, events=events)
-        return single(depth, K, masks, ground, w["method"], w["yaw_steps"], seed=1234, events=events)
+        if fitter is not None and events is None:
+            return fitter(depth, K, masks, ground, w["method"], w["yaw_steps"], seed=1234)
+        # per-kernel timing (events) is a local matter: this rank's block without the gather
+        return single(depth, K, masks, ground, w["method"], w["yaw_steps"], seed=1234, image_offset=B * rank, events=events)
 
     def fence():
         torch.cuda.synchronize()
@@ -324,7 +331,7 @@ def main():
             "metric": METRIC, "value": boxes_per_step * args.steps / (ms_total * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(world),
+            "config": config_dict(world, args.collective),
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,
             "kernels_ms": {"fit_prepare": k_prep, "mask_scan": k_scan, "sample_ranks": k_samp, "fit_boxes": k_fit,

@@ -159,6 +159,24 @@ int la3d_fit_boxes(const float* depth, const uint8_t* masks, const double* K, co
                    void* workspace, size_t workspace_bytes, void* records, int rec_f64, la3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Multi-GPU form (images sharded across the GPUs of one NVLink / NVSwitch node, the reference's
+ * --start_index/--end_index/--gpu_idx split of src/batch_scripts/whole.py:25-27,42): the fit kernel
+ * writes every record straight into the gathered record buffer of EVERY rank through peer memory
+ * (peer_records[p] = rank p's gathered buffer + this rank's slot; include the local one), so the
+ * all-gather costs no extra pass; la3d_peer_barrier then tells each rank that all slots have landed.
+ *   peer_records: HOST array of n_peers (<= LA3D_MAX_PEERS) device pointers, peer-mapped
+ *   flags:        HOST array of `world` device pointers; flags[p] = rank p's array of >= world uint32
+ *                 (peer-mapped, zero-initialised once); epoch must grow by one per barrier
+ *   status:       nullable device int, set to 1 if a peer did not arrive within ~2 s
+ * ------------------------------------------------------------------------- */
+#define LA3D_MAX_PEERS 8
+int la3d_fit_boxes_p2p(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
+                       int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed, uint32_t image_offset,
+                       void* workspace, size_t workspace_bytes, void* const* peer_records, int n_peers, int rec_f64,
+                       la3d_stream_t stream);
+int la3d_peer_barrier(uint32_t* const* flags, int rank, int world, uint32_t epoch, int* status, la3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Oriented box from explicit point sets.  Replaces estimate_bbox,
  * src/util_3dbox.py:106-178, for the way the reference itself calls it (500
  * points sampled from a mesh, src/util_3dbox.py:269-278).

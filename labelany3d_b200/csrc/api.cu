@@ -22,6 +22,10 @@ int cuda_fail(cudaError_t err, const char* what) {
   return LA3D_ECUDA;
 }
 
+struct PeerFlags {
+  uint32_t* flags[LA3D_MAX_PEERS];
+};
+
 struct Workspace {
   uint32_t* bits;
   uint32_t* chunk_counts;
@@ -59,11 +63,11 @@ extern "C" size_t la3d_fit_workspace_bytes(int B, int I, int H, int W) {
   return la3d::carve(nullptr, B, I, H, W).bytes;
 }
 
-extern "C" int la3d_fit_boxes(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
-                              int I, int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
-                              uint32_t image_offset, void* workspace, size_t workspace_bytes, void* records,
-                              int rec_f64, la3d_stream_t stream) {
-  using namespace la3d;
+namespace la3d {
+static int fit_boxes_multi(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
+                           int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
+                           uint32_t image_offset, void* workspace, size_t workspace_bytes, void* const* records,
+                           int n_out, int rec_f64, la3d_stream_t stream) {
   LA3D_REQUIRE(depth && masks && K && workspace && records, "null pointer");
   LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
@@ -81,6 +85,58 @@ extern "C" int la3d_fit_boxes(const float* depth, const uint8_t* masks, const do
   if (rc) return rc;
   rc = la3d_sample_ranks(w.chunk_counts, w.prep, B, I, H, W, w.counts, w.ranks, stream);
   if (rc) return rc;
-  return la3d_fit_scanned(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, records,
-                          rec_f64, stream);
+  return fit_scanned_multi(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, records, n_out,
+                           rec_f64, static_cast<cudaStream_t>(stream));
+}
+
+// Cross-GPU barrier over peer memory: rank r stores `epoch` into slot r of every peer's flag array
+// (release, system scope), then waits until every slot of its own array has reached `epoch`.
+// Epochs only grow, so the flags never need a reset.  status[0] is set to 1 if a peer does not show up
+// within ~2 s (the kernel returns instead of hanging the GPU).
+__global__ void peer_barrier_kernel(PeerFlags pf, int rank, int world, uint32_t epoch, int* status) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.flags[p] + rank), "r"(epoch) : "memory");
+  const uint32_t* mine = pf.flags[rank] + p;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int32_t)(v - epoch) >= 0) break;
+    if (clock64() - t0 > 4000000000ll) { if (status) *status = 1; break; }
+    __nanosleep(64);
+  }
+}
+}  // namespace la3d
+
+extern "C" int la3d_fit_boxes(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
+                              int I, int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
+                              uint32_t image_offset, void* workspace, size_t workspace_bytes, void* records,
+                              int rec_f64, la3d_stream_t stream) {
+  return la3d::fit_boxes_multi(depth, masks, K, ground, B, I, H, W, mask_is_01, method, yaw_steps, seed, image_offset,
+                               workspace, workspace_bytes, &records, 1, rec_f64, stream);
+}
+
+extern "C" int la3d_fit_boxes_p2p(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
+                                  int I, int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
+                                  uint32_t image_offset, void* workspace, size_t workspace_bytes,
+                                  void* const* peer_records, int n_peers, int rec_f64, la3d_stream_t stream) {
+  return la3d::fit_boxes_multi(depth, masks, K, ground, B, I, H, W, mask_is_01, method, yaw_steps, seed, image_offset,
+                               workspace, workspace_bytes, peer_records, n_peers, rec_f64, stream);
+}
+
+extern "C" int la3d_peer_barrier(uint32_t* const* flags, int rank, int world, uint32_t epoch, int* status,
+                                 la3d_stream_t stream) {
+  using namespace la3d;
+  LA3D_REQUIRE(flags, "null pointer");
+  LA3D_REQUIRE(world >= 1 && world <= LA3D_MAX_PEERS && rank >= 0 && rank < world, "bad rank / world");
+  PeerFlags pf{};
+  for (int p = 0; p < world; ++p) {
+    LA3D_REQUIRE(flags[p] != nullptr, "null flag array");
+    pf.flags[p] = flags[p];
+  }
+  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, rank, world, epoch, status);
+  LA3D_CUDA(cudaGetLastError());
+  return LA3D_OK;
 }

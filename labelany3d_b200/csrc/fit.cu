@@ -50,9 +50,18 @@ struct FitArgs {
   const double* K;        // [images or boxes][9] intrinsics; may be null for explicit points
   const double* ground;   // [boxes][3] or null
   int method, yaw_steps, n_areas;
-  void* records;
+  void* records[LA3D_MAX_PEERS];   // the record of box j goes to records[p] + j*64 for every p < n_out:
+  int n_out;                       // one local buffer, or the gathered buffers of all ranks (peer memory)
   int rec_f64;
 };
+
+__device__ __forceinline__ void put_record(const FitArgs& a, size_t idx, double val) {
+#pragma unroll 1
+  for (int p = 0; p < a.n_out; ++p) {
+    if (a.rec_f64) reinterpret_cast<double*>(a.records[p])[idx] = val;
+    else reinterpret_cast<float*>(a.records[p])[idx] = (float)val;
+  }
+}
 
 // Static shared memory.  The y coordinate is not kept: only its minimum / maximum matter (they do
 // not depend on the yaw) and those are reduced on the fly.
@@ -533,8 +542,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
       if (f == LA3D_O_STATUS) val = (double)status;
       if (f == LA3D_O_NMASK) val = (double)n_src;
       if (f == LA3D_O_PAD) val = 0.0;
-      if (a.rec_f64) reinterpret_cast<double*>(a.records)[(size_t)box * LA3D_REC + f] = val;
-      else reinterpret_cast<float*>(a.records)[(size_t)box * LA3D_REC + f] = (float)val;
+      put_record(a, (size_t)box * LA3D_REC + f, val);
     }
     return;
   }
@@ -664,10 +672,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
     rec[LA3D_O_BOX2D + 2] = mxu; rec[LA3D_O_BOX2D + 3] = mxv;
   }
   __syncthreads();
-  for (int f = tid; f < LA3D_REC; f += kThreads) {
-    if (a.rec_f64) reinterpret_cast<double*>(a.records)[(size_t)box * LA3D_REC + f] = rec[f];
-    else reinterpret_cast<float*>(a.records)[(size_t)box * LA3D_REC + f] = (float)rec[f];
-  }
+  for (int f = tid; f < LA3D_REC; f += kThreads) put_record(a, (size_t)box * LA3D_REC + f, rec[f]);
 }
 
 int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s) {
@@ -694,11 +699,12 @@ int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s) {
 }  // namespace
 }  // namespace la3d
 
-extern "C" int la3d_fit_scanned(const float* depth, const void* prep, const uint32_t* bits,
-                                const uint32_t* chunk_counts, const int32_t* ranks, int B, int I, int H, int W,
-                                int method, int yaw_steps, void* records, int rec_f64, la3d_stream_t stream) {
-  using namespace la3d;
+namespace la3d {
+int fit_scanned_multi(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
+                      const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
+                      void* const* records, int n_out, int rec_f64, cudaStream_t stream) {
   LA3D_REQUIRE(depth && prep && bits && chunk_counts && ranks && records, "null pointer");
+  LA3D_REQUIRE(n_out >= 1 && n_out <= LA3D_MAX_PEERS, "between 1 and LA3D_MAX_PEERS output buffers");
   LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
   LA3D_REQUIRE(method != LA3D_METHOD_SWEEP || (yaw_steps > 0 && yaw_steps <= 16384), "sweep needs 1 <= yaw_steps <= 16384");
@@ -707,8 +713,21 @@ extern "C" int la3d_fit_scanned(const float* depth, const void* prep, const uint
   a.depth = depth; a.bits = bits; a.chunk_counts = chunk_counts; a.ranks = ranks;
   a.cams = pv.cams; a.Rg_pre = pv.Rg;
   a.I = I; a.HW = H * W; a.W = W; a.chunks = (int)la3d_chunks_per_plane(H, W);
-  a.method = method; a.yaw_steps = yaw_steps; a.records = records; a.rec_f64 = rec_f64;
-  return launch_fit(true, a, B * I, static_cast<cudaStream_t>(stream));
+  a.method = method; a.yaw_steps = yaw_steps; a.rec_f64 = rec_f64;
+  for (int p = 0; p < n_out; ++p) {
+    LA3D_REQUIRE(records[p] != nullptr, "null output buffer");
+    a.records[p] = records[p];
+  }
+  a.n_out = n_out;
+  return launch_fit(true, a, B * I, stream);
+}
+}  // namespace la3d
+
+extern "C" int la3d_fit_scanned(const float* depth, const void* prep, const uint32_t* bits,
+                                const uint32_t* chunk_counts, const int32_t* ranks, int B, int I, int H, int W,
+                                int method, int yaw_steps, void* records, int rec_f64, la3d_stream_t stream) {
+  return la3d::fit_scanned_multi(depth, prep, bits, chunk_counts, ranks, B, I, H, W, method, yaw_steps, &records, 1,
+                                 rec_f64, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int la3d_fit_points(const double* pts, const int64_t* offsets, const int32_t* sample_idx, const double* K,
@@ -720,6 +739,7 @@ extern "C" int la3d_fit_points(const double* pts, const int64_t* offsets, const 
   LA3D_REQUIRE(method != LA3D_METHOD_SWEEP || (yaw_steps > 0 && yaw_steps <= 16384), "sweep needs 1 <= yaw_steps <= 16384");
   FitArgs a{};
   a.pts = pts; a.offsets = offsets; a.sample_idx = sample_idx;
-  a.K = K; a.ground = ground; a.method = method; a.yaw_steps = yaw_steps; a.records = records; a.rec_f64 = rec_f64;
+  a.K = K; a.ground = ground; a.method = method; a.yaw_steps = yaw_steps; a.records[0] = records; a.n_out = 1;
+  a.rec_f64 = rec_f64;
   return launch_fit(false, a, nboxes, static_cast<cudaStream_t>(stream));
 }

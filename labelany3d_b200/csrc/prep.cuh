@@ -105,4 +105,8 @@ __device__ __forceinline__ void prep_body(const PrepArgs& pa, int b) {
 int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
                      uint32_t* chunk_counts, const PrepArgs* prep, cudaStream_t s);
 
+int fit_scanned_multi(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
+                      const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
+                      void* const* records, int n_out, int rec_f64, cudaStream_t stream);
+
 }  // namespace la3d

@@ -10,6 +10,8 @@ The per-image RNG seed (``seed + global image index``) makes the result independ
 
 from __future__ import annotations
 
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -48,9 +50,19 @@ def all_gather_records(local, total=None, group=None):
 
 
 class ShardedBoxFitter:
-    """``BoxFitter`` for this rank's block of a ``B_total``-image batch plus the final all-gather."""
+    """``BoxFitter`` for this rank's block of a ``B_total``-image batch plus the gather of the records.
 
-    def __init__(self, B_total, I, H, W, device=None, out_dtype=torch.float64, group=None):
+    ``collective="p2p"`` (default on CUDA with more than one rank): the gathered ``[world*per, I, 64]``
+    buffer of every rank lives in symmetric (peer-mapped) memory and the fit kernel of rank ``r``
+    writes its records directly into slot ``r`` of EVERY rank's buffer over NVLink
+    (``la3d_fit_boxes_p2p``); a flag barrier over peer memory (``la3d_peer_barrier``) then tells each
+    rank that all slots have landed.  No separate collective pass, no NCCL launch on the data path.
+    The gathered buffer is double-buffered: the tensor a call returns stays valid until the
+    next-but-one call (consume it on the same stream).
+    ``collective="nccl"``: one ``all_gather_into_tensor`` after the fit (the plain form).
+    """
+
+    def __init__(self, B_total, I, H, W, device=None, out_dtype=torch.float64, group=None, collective=None):
         from .ops import BoxFitter
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -59,13 +71,72 @@ class ShardedBoxFitter:
         self.start, self.stop, self.per = shard_range(self.B_total, self.rank, self.world)
         self.n_local = self.stop - self.start
         device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.out_dtype = out_dtype
+        self.I = int(I)
         self.local = BoxFitter(max(self.n_local, 1), I, H, W, device=device, out_dtype=out_dtype)
-        self.gathered = torch.empty((self.world * self.per, I, REC), dtype=out_dtype, device=device)
-        self.slot = torch.full((self.per, I, REC), float("nan"), dtype=out_dtype, device=device)
-        self.slot[..., O_STATUS] = -1
+        if collective is None:
+            collective = "p2p" if self.world > 1 else "none"
+        if collective not in ("p2p", "nccl", "none"):
+            raise ValueError(f"collective must be 'p2p', 'nccl' or 'none', got {collective!r}")
+        if self.world == 1:
+            collective = "none"
+        self.collective = collective
+        if collective == "p2p":
+            self._init_p2p()
+        else:
+            self.gathered = torch.empty((self.world * self.per, I, REC), dtype=out_dtype, device=device)
+            self.slot = torch.full((self.per, I, REC), float("nan"), dtype=out_dtype, device=device)
+            self.slot[..., O_STATUS] = -1
+
+    # -- peer memory ---------------------------------------------------------------------------
+    def _init_p2p(self):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        if self.world > 8:
+            raise ValueError("the peer-memory gather supports at most 8 ranks (one NVLink node)")
+        grp = self.group if self.group is not None else dist.group.WORLD
+        shape = (self.world * self.per, self.I, REC)
+        self._bufs, self._peer_slots = [], []
+        esize = torch.empty((), dtype=self.out_dtype).element_size()
+        slot_bytes = self.per * self.I * REC * esize
+        for _ in range(2):                                   # double buffer (see the class docstring)
+            t = symm.empty(shape, dtype=self.out_dtype, device=self.device)
+            t.fill_(float("nan"))
+            t[..., O_STATUS] = -1
+            hdl = symm.rendezvous(t, grp)
+            self._bufs.append((t, hdl))
+            self._peer_slots.append([int(p) + self.rank * slot_bytes for p in hdl.buffer_ptrs])
+        f = symm.empty((64,), dtype=torch.int32, device=self.device)
+        f.zero_()
+        fh = symm.rendezvous(f, grp)
+        self._flags, self._flag_hdl = f, fh
+        self._flag_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in fh.buffer_ptrs])
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._epoch = 0
+        self._lib = _lib.load()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)                       # every rank's fills have landed before the first step
+
+    def check_barrier_status(self):
+        """Raises if a peer failed to arrive at a barrier (synchronises the device)."""
+        if self.collective == "p2p" and int(self._status.item()) != 0:
+            raise RuntimeError("la3d_peer_barrier: a peer did not arrive within the timeout")
 
     def __call__(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, events=None):
         """Inputs are this rank's block (``[n_local, ...]``).  Returns ``[B_total, I, 64]`` on every rank."""
+        if self.collective == "p2p":
+            from . import _lib
+            self._epoch += 1
+            buf, _ = self._bufs[self._epoch & 1]
+            if self.n_local:
+                peers = self._peer_slots[self._epoch & 1]
+                self.local(depth, K, masks, ground, method, yaw_steps, seed, image_offset=self.start, peers=peers)
+            with torch.cuda.device(self.device):
+                rc = self._lib.la3d_peer_barrier(self._flag_ptrs, self.rank, self.world, self._epoch & 0xFFFFFFFF,
+                                                 self._status.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "la3d_peer_barrier")
+            return buf[:self.B_total]
         if self.n_local:
             self.local(depth, K, masks, ground, method, yaw_steps, seed, image_offset=self.start,
                        out=self.slot[:self.n_local], events=events)

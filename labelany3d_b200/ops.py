@@ -8,6 +8,8 @@ streams only.  Inputs must live on a CUDA device; nothing falls back to the CPU.
 
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 import torch
 
@@ -188,12 +190,14 @@ class BoxFitter:
         self.records = torch.empty((B, I, REC), dtype=out_dtype, device=self.device)
 
     def __call__(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0, out=None,
-                 events=None):
+                 events=None, peers=None):
         """Fit every (image, instance) box; returns ``records[B,I,64]`` (a buffer owned by the plan
         unless ``out`` is given).  ``events``: optional list of 5 ``torch.cuda.Event``; the four kernels
         are then issued one after the other on the current stream (no overlap) with the events
         recorded before, between and after them: prepare, scan, sample, fit (per-kernel timing
-        without a profiler)."""
+        without a profiler).  ``peers``: list of device pointers (ints) of ``[B,I,64]`` slots in
+        peer-mapped record buffers; the fit kernel then writes every record to all of them
+        (``la3d_fit_boxes_p2p``) instead of to ``out``."""
         B, I, H, W = self.shape
         depth = _need_cuda("depth", depth, torch.float32)
         K = _need_cuda("K", K, torch.float64)
@@ -213,7 +217,16 @@ class BoxFitter:
         lib = self.lib
         with torch.cuda.device(self.device):
             st = _stream()
-            if events is None:
+            if peers is not None:
+                if events is not None:
+                    raise ValueError("events and peers are mutually exclusive")
+                arr = (ctypes.c_void_p * len(peers))(*peers)
+                rc = lib.la3d_fit_boxes_p2p(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01,
+                                            _method_id(method), int(yaw_steps), int(seed) & 0xFFFFFFFF,
+                                            int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace), self.ws_bytes,
+                                            arr, len(peers), f64, st)
+                _lib.check(rc, "la3d_fit_boxes_p2p")
+            elif events is None:
                 rc = lib.la3d_fit_boxes(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01,
                                         _method_id(method), int(yaw_steps), int(seed) & 0xFFFFFFFF,
                                         int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace), self.ws_bytes,
