@@ -106,6 +106,24 @@ int la3d_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_0
                    uint32_t* chunk_counts, la3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Mask statistics on the bit planes of la3d_mask_scan ("next" row f1 of the scope table): the
+ * integer bookkeeping of analyze_mask (src/util.py:291-326), get_maximum_height
+ * (src/util.py:328-335), the row count of src/util.py:369-370 and the overlap counts of
+ * filter_component_masks (src/model_wrappers.py:33-37).
+ *   bands  HOST array of 8 ints: rows [t0,t1) = top band, rows [b0,b1) = bottom band, columns
+ *          [l0,l1) = left band, columns [r0,r1) = right band (the caller resolves the reference's
+ *          Python slices `[:b]` / `[-b:]` against H and W)
+ *   stats  [planes][8] int32 (out): area, pixels in the top / bottom / left / right band, first
+ *          non-empty row (-1 if none), last non-empty row (-1 if none), number of non-empty rows
+ *   la3d_mask_overlap: inter[p] = |bits[p] & other_bits[p / group]| (group = instances per image
+ *          when every image has one foreground plane)
+ * ------------------------------------------------------------------------- */
+int la3d_mask_stats(const uint32_t* bits, int planes, int H, int W, const int* bands, int32_t* stats,
+                    la3d_stream_t stream);
+int la3d_mask_overlap(const uint32_t* bits, const uint32_t* other_bits, int planes, int group, int H, int W,
+                      int32_t* inter, la3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Mask-independent preparation of a batch for the scanned-mask path.  Everything the
  * sampler and the fit kernel need that does not depend on the masks, so that it can run
  * concurrently with the mask scan (la3d_fit_boxes folds it into the scan's launch):
@@ -200,6 +218,38 @@ int la3d_fit_points(const double* pts, const int64_t* offsets, const int32_t* sa
  * ------------------------------------------------------------------------- */
 int la3d_project_points(const double* pts, const double* K, const int32_t* k_index, long long n, double* uv,
                         la3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Combine stage ("next" row f2): src/tools/combine_results.py of the reference.
+ * la3d_iou_matrix replaces iou2D (:111-123) over all pairs of two box lists, i.e. the cost
+ * matrix of hungarian_matching (:130-134), for `groups` scenes in one launch:
+ *   boxes0 [total0][4], boxes1 [total1][4] double xyxy; off0 / off1 [groups+1] int64 row offsets
+ *   iou    (out) concatenated row-major [n0_g][n1_g] blocks, block g at iou + out_off[g]
+ * Same operation order as the Python floats, no FMA: bit-identical.  The assignment itself
+ * (scipy linear_sum_assignment, :137) stays on the host.
+ * la3d_box2d_from_corners replaces :234-252: corners [n][8][3] double, K [m][9], k_index nullable
+ * [n] int32 (which K / image size a box uses), wh [m][2] = (W, H) double ->
+ * proj [n][4] = [min u, min v, max u, max v], trunc [n][4] = [max(0,.), max(0,.), min(W,.), min(H,.)]
+ * with Python's min()/max() NaN behaviour.
+ * ------------------------------------------------------------------------- */
+int la3d_iou_matrix(const double* boxes0, const int64_t* off0, const double* boxes1, const int64_t* off1,
+                    const int64_t* out_off, int groups, double* iou, la3d_stream_t stream);
+int la3d_box2d_from_corners(const double* corners, const double* K, const int32_t* k_index, const double* wh, int n,
+                            double* proj, double* trunc, la3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Depth-scale alignment ("next" row f3): the arithmetic of align_to_depth_match,
+ * src/util.py:473-486: per plane p, over the pixels of mask_bits[p] & render_bits[p],
+ * scale[p] = np.median(depth_map[p / group] / depth_render[p]) in float32 (exact radix
+ * select; an even count averages the two middle values like np.median; NaN if any ratio is
+ * NaN) and n_overlap[p] = number of such pixels (0: the reference returns the identity
+ * transform, scale[p] is NaN).
+ *   depth_map [planes/group][H][W] float; depth_render [planes][H][W] float
+ *   mask_bits / render_bits: bit planes of la3d_mask_scan
+ * ------------------------------------------------------------------------- */
+int la3d_masked_ratio_median(const float* depth_map, const float* depth_render, const uint32_t* mask_bits,
+                             const uint32_t* render_bits, int planes, int group, int H, int W, int32_t* n_overlap,
+                             float* scale, la3d_stream_t stream);
 
 #ifdef __cplusplus
 }

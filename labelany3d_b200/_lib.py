@@ -20,6 +20,8 @@ SIGNATURES = {
     "la3d_chunks_per_plane": (_sz, [_i, _i]),
     "la3d_words_per_plane": (_sz, [_i, _i]),
     "la3d_mask_scan": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "la3d_mask_stats": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "la3d_mask_overlap": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "la3d_prep_bytes": (_sz, [_i, _i]),
     "la3d_fit_prepare": (_i, [_vp, _vp, _i, _i, _u32, _u32, _vp, _sz, _vp]),
     "la3d_set_mt_blocks": (None, [_i]),
@@ -30,6 +32,9 @@ SIGNATURES = {
     "la3d_fit_boxes_p2p": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _i, _i, _vp]),
     "la3d_peer_barrier": (_i, [_vp, _i, _i, _u32, _vp, _vp]),
     "la3d_fit_points": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "la3d_iou_matrix": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "la3d_box2d_from_corners": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "la3d_masked_ratio_median": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "la3d_project_points": (_i, [_vp, _vp, _vp, C.c_longlong, _vp, _vp]),
 }
 

@@ -1,9 +1,11 @@
-"""Drop-in for the three hot-path functions of the reference's ``src/util.py``:
-``depth_to_points`` (``:52-75``), ``project_to_2d`` (``:227-229``) and ``draw_cube``
-(``:232-289``).  Same names, signatures and return types; the arithmetic runs on the B200.
+"""Drop-in for the hot-path functions of the reference's ``src/util.py``:
+``depth_to_points`` (``:52-75``), ``project_to_2d`` (``:227-229``), ``draw_cube`` (``:232-289``)
+and, either side of the box fit, ``analyze_mask`` (``:291-326``), ``get_maximum_height``
+(``:328-335``) and ``align_to_depth_match`` (``:464-494``).  Same names, signatures and return
+types; the arithmetic runs on the B200.
 
-Only these three are provided: the rest of the reference's ``util.py`` is model / IO glue
-outside this path.
+Only these are provided: the rest of the reference's ``util.py`` is model / IO glue outside this
+path.
 """
 
 from __future__ import annotations
@@ -78,3 +80,70 @@ def draw_cube(scene_dir, is_ground=False):
         cv2.putText(image, f'{cube["category_name"]}', (int(uv[top][0]), int(uv[top][1]) - 10),
                     cv2.FONT_HERSHEY_SIMPLEX, 0.5, (0, 0, 255), 1)
     cv2.imwrite(os.path.join(scene_dir, "vis_3dbox.png" if is_ground else "vis_3dbox_no_ground.png"), image)
+
+
+# ---------------------------------------------------------------------------------------------
+# mask statistics (scope table row f1)
+# ---------------------------------------------------------------------------------------------
+def _plane_stats(mask, boundary_threshold=10):
+    dev = _device()
+    m = np.asarray(mask)
+    if m.ndim != 2:
+        raise ValueError(f"expected a mask of shape [H,W], got {m.shape}")
+    t = torch.as_tensor(np.ascontiguousarray(m != 0), device=dev)
+    bits, _ = _ops.mask_scan(t[None])
+    return _ops.mask_stats(bits, m.shape[0], m.shape[1], boundary_threshold)[0].cpu().numpy()
+
+
+def analyze_mask(mask, image_size, scale_threshold=100, boundary_threshold=10):
+    """``(is_truncated, is_scaleable)``: does the mask put at least 10 pixels into the border bands,
+    and does it cover at least ``scale_threshold`` pixels (``src/util.py:291-326``).  The counts
+    come from one pass over the mask on the GPU (``la3d_mask_scan`` + ``la3d_mask_stats``)."""
+    mask = np.asarray(mask)
+    if not np.array_equal(mask, mask.astype(bool)):
+        raise ValueError("Image Mask must be binary (contain only 0s and 1s).")
+    s = _plane_stats(mask, boundary_threshold)
+    total_truncation = int(s[_ops.STAT_TOP]) + int(s[_ops.STAT_BOTTOM]) + int(s[_ops.STAT_LEFT]) + int(s[_ops.STAT_RIGHT])
+    return total_truncation >= 10, int(s[_ops.STAT_AREA]) >= scale_threshold
+
+
+def get_maximum_height(binary_mask):
+    """Last minus first non-empty row plus one, 0 for an empty mask (``src/util.py:328-335``)."""
+    s = _plane_stats(binary_mask)
+    if s[_ops.STAT_ROWS] == 0:
+        return 0
+    return np.int64(int(s[_ops.STAT_LAST_ROW]) - int(s[_ops.STAT_FIRST_ROW]) + 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# depth-scale alignment (scope table row f3)
+# ---------------------------------------------------------------------------------------------
+def align_to_depth_match(mask, depth_map, object_name, project_root, model):
+    """4x4 transform that rescales a reconstructed object to the scene depth
+    (``src/util.py:464-494``): the matcher the reference calls (``matching.process_image_space``,
+    outside this path) renders the object; the scale is the median of ``depth_map / rendered
+    depth`` over ``mask & rendered alpha > 0``, computed on the GPU straight from the bit planes
+    (``la3d_masked_ratio_median``, bit-exact with ``np.median`` on float32)."""
+    from matching.process_image_space import process_object
+    R, T, image_render, depth = process_object(object_name, project_root, model)
+    render_mask = image_render[..., -1] > 0
+    dev = _device()
+    mask = np.asarray(mask)
+    H, W = mask.shape
+    both = torch.as_tensor(np.ascontiguousarray(np.stack([mask != 0, render_mask])), device=dev)
+    bits, _ = _ops.mask_scan(both)
+    dm = np.asarray(depth_map)
+    dr = np.asarray(depth)
+    if dm.dtype != np.float32 or dr.dtype != np.float32:
+        raise TypeError("align_to_depth_match: the GPU path takes float32 depth maps (what the pipeline stores)")
+    n, scale = _ops.depth_scale_median(torch.as_tensor(np.ascontiguousarray(dm), device=dev)[None],
+                                       torch.as_tensor(np.ascontiguousarray(dr), device=dev)[None, None],
+                                       bits[0:1], bits[1:2], H, W)
+    if int(n.item()) == 0:
+        print("No overlap between masks found")
+        return np.eye(4)
+    scale = scale.cpu().numpy()[0, 0]
+    transform = np.eye(4)
+    transform[:3, :3] = np.linalg.inv(R[:3, :3]) * scale
+    transform[:3, -1] = T[:3] * scale
+    return transform

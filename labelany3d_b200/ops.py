@@ -112,6 +112,49 @@ def mask_scan(masks):
     return bits, cc
 
 
+STAT_AREA, STAT_TOP, STAT_BOTTOM, STAT_LEFT, STAT_RIGHT, STAT_FIRST_ROW, STAT_LAST_ROW, STAT_ROWS = range(8)
+
+
+def mask_stats(bits, H, W, boundary_threshold=10):
+    """Per-plane integer statistics from the bit planes of :func:`mask_scan` (``la3d_mask_stats``).
+
+    Returns ``stats[P, 8]`` int32: area, pixels inside the top / bottom / left / right border band
+    (``analyze_mask``, ``src/util.py:303-320`` of the reference: bands ``[:b]`` and ``[-b:]`` with
+    Python slice semantics, so ``b = 0`` makes the bottom / right band the whole image), first and
+    last non-empty row (-1 if the mask is empty), number of non-empty rows.
+    """
+    lib = _lib.load()
+    bits = _need_cuda("bits", bits, torch.int32)
+    planes = bits.shape[0]
+    b = int(boundary_threshold)
+    t0, t1, _ = slice(None, b).indices(H)
+    b0, b1, _ = slice(-b, None).indices(H)
+    l0, l1, _ = slice(None, b).indices(W)
+    r0, r1, _ = slice(-b, None).indices(W)
+    bands = (ctypes.c_int * 8)(t0, max(t1, t0), b0, max(b1, b0), l0, max(l1, l0), r0, max(r1, r0))
+    stats = torch.empty((planes, 8), dtype=torch.int32, device=bits.device)
+    with torch.cuda.device(bits.device):
+        rc = lib.la3d_mask_stats(_ptr(bits), planes, H, W, bands, _ptr(stats), _stream())
+    _lib.check(rc, "la3d_mask_stats")
+    return stats
+
+
+def mask_overlap(bits, other_bits, H, W, group=1):
+    """``inter[p] = |bits[p] & other_bits[p // group]|`` (``la3d_mask_overlap``): the numerator of
+    ``filter_component_masks`` (``src/model_wrappers.py:36`` of the reference)."""
+    lib = _lib.load()
+    bits = _need_cuda("bits", bits, torch.int32)
+    other_bits = _need_cuda("other_bits", other_bits, torch.int32)
+    planes = bits.shape[0]
+    if other_bits.shape[0] * group < planes or other_bits.shape[1] != bits.shape[1]:
+        raise ValueError("other_bits must hold one plane per group of `group` planes, same image size")
+    inter = torch.empty((planes,), dtype=torch.int32, device=bits.device)
+    with torch.cuda.device(bits.device):
+        rc = lib.la3d_mask_overlap(_ptr(bits), _ptr(other_bits), planes, int(group), H, W, _ptr(inter), _stream())
+    _lib.check(rc, "la3d_mask_overlap")
+    return inter
+
+
 def fit_prepare(K, ground, B, I, seed=0, image_offset=0):
     """Mask-independent preparation of a batch (``la3d_fit_prepare``): per-image MT19937 words,
     intrinsics and their inverse, per-box ground rotations.  Returns the opaque ``prep`` buffer
@@ -341,6 +384,82 @@ def project_points(points, K, k_index=None):
         rc = lib.la3d_project_points(_ptr(points), _ptr(K), _ptr(k_index), n, _ptr(uv), _stream())
     _lib.check(rc, "la3d_project_points")
     return uv
+
+
+def iou_matrix(boxes0, boxes1, off0=None, off1=None):
+    """Pairwise ``iou2D`` (``src/tools/combine_results.py:111-123`` of the reference) of two xyxy box
+    lists, float64, bit-identical to the Python floats.  Without offsets: ``[n0,4] x [n1,4] -> [n0,n1]``.
+    With ``off0`` / ``off1`` (``[G+1]`` int64 row offsets): one block per scene, all scenes in one
+    launch; returns ``(flat, out_off)`` with block ``g`` = ``flat[out_off[g]:out_off[g+1]].view(n0_g, n1_g)``."""
+    lib = _lib.load()
+    boxes0 = _need_cuda("boxes0", boxes0, torch.float64)
+    boxes1 = _need_cuda("boxes1", boxes1, torch.float64)
+    dev = boxes0.device
+    single = off0 is None
+    if single:
+        off0 = torch.tensor([0, boxes0.shape[0]], dtype=torch.int64, device=dev)
+        off1 = torch.tensor([0, boxes1.shape[0]], dtype=torch.int64, device=dev)
+    off0 = _need_cuda("off0", off0, torch.int64)
+    off1 = _need_cuda("off1", off1, torch.int64)
+    G = off0.numel() - 1
+    sizes = (off0[1:] - off0[:-1]) * (off1[1:] - off1[:-1])
+    out_off = torch.zeros(G + 1, dtype=torch.int64, device=dev)
+    out_off[1:] = torch.cumsum(sizes, 0)
+    total = int(out_off[-1].item())
+    flat = torch.empty((max(total, 1),), dtype=torch.float64, device=dev)
+    if total:
+        with torch.cuda.device(dev):
+            rc = lib.la3d_iou_matrix(_ptr(boxes0), _ptr(off0), _ptr(boxes1), _ptr(off1), _ptr(out_off), G, _ptr(flat),
+                                     _stream())
+        _lib.check(rc, "la3d_iou_matrix")
+    flat = flat[:total]
+    if single:
+        return flat.view(boxes0.shape[0], boxes1.shape[0])
+    return flat, out_off
+
+
+def box2d_from_corners(corners, K, wh, k_index=None):
+    """``bbox2D_proj`` / ``bbox2D_trunc`` (``src/tools/combine_results.py:234-252``) of boxes given by
+    their corners ``[n,8,3]``; ``K[m,3,3]``, ``wh[m,2] = (W, H)``, ``k_index[n]`` int32 picks the image."""
+    lib = _lib.load()
+    corners = _need_cuda("corners", corners, torch.float64)
+    K = _need_cuda("K", K, torch.float64)
+    wh = _need_cuda("wh", wh, torch.float64)
+    n = corners.shape[0]
+    if k_index is not None:
+        k_index = _need_cuda("k_index", k_index, torch.int32)
+    proj = torch.empty((n, 4), dtype=torch.float64, device=corners.device)
+    trunc = torch.empty((n, 4), dtype=torch.float64, device=corners.device)
+    if n:
+        with torch.cuda.device(corners.device):
+            rc = lib.la3d_box2d_from_corners(_ptr(corners), _ptr(K), _ptr(k_index), _ptr(wh), n, _ptr(proj), _ptr(trunc),
+                                             _stream())
+        _lib.check(rc, "la3d_box2d_from_corners")
+    return proj, trunc
+
+
+def depth_scale_median(depth_map, depth_render, mask_bits, render_bits, H, W):
+    """Per plane the median of ``depth_map / depth_render`` over ``mask & render_mask``
+    (``align_to_depth_match``, ``src/util.py:473-486`` of the reference), float32, bit-exact with
+    ``np.median``.  ``depth_map[B,H,W]``, ``depth_render[B,I,H,W]`` float32; bit planes ``[B*I, words]``
+    from :func:`mask_scan`.  Returns ``(n_overlap[B,I] int32, scale[B,I] float32)``; ``scale`` is NaN
+    where the overlap is empty (the reference returns the identity transform there)."""
+    lib = _lib.load()
+    depth_map = _need_cuda("depth_map", depth_map, torch.float32)
+    depth_render = _need_cuda("depth_render", depth_render, torch.float32)
+    mask_bits = _need_cuda("mask_bits", mask_bits, torch.int32)
+    render_bits = _need_cuda("render_bits", render_bits, torch.int32)
+    B, I = depth_render.shape[:2]
+    planes = B * I
+    if depth_map.shape[0] != B or mask_bits.shape[0] != planes or render_bits.shape[0] != planes:
+        raise ValueError("shape mismatch between depth maps and bit planes")
+    n = torch.empty((B, I), dtype=torch.int32, device=depth_map.device)
+    scale = torch.empty((B, I), dtype=torch.float32, device=depth_map.device)
+    with torch.cuda.device(depth_map.device):
+        rc = lib.la3d_masked_ratio_median(_ptr(depth_map), _ptr(depth_render), _ptr(mask_bits), _ptr(render_bits), planes,
+                                          I, H, W, _ptr(n), _ptr(scale), _stream())
+    _lib.check(rc, "la3d_masked_ratio_median")
+    return n, scale
 
 
 def to_numpy(t):
