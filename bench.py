@@ -344,7 +344,8 @@ def main():
         }
         traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(traffic_path):
-            line["roofline"]["traffic"] = json.load(open(traffic_path)).get("mask_scan_kernel")
+            t = json.load(open(traffic_path)).get("mask_scan_kernel<1, 1, 1>")     # the scan with the prep CTAs in its grid
+            line["roofline"]["traffic"] = t[0] if isinstance(t, list) else t
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
         else:

@@ -105,6 +105,14 @@ size_t la3d_words_per_plane(int H, int W);
 int la3d_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
                    uint32_t* chunk_counts, la3d_stream_t stream);
 
+/* The same scan as a "thin" persistent kernel: ctas_per_sm CTAs per SM whose loads are issued by the
+ * TMA unit (cp.async.bulk into a ring of `stages` 16 KB shared-memory stages, mbarrier-signalled),
+ * so it reaches the same bandwidth with ~1/4 of the resident threads and leaves room on every SM for
+ * the sampler / fit kernels of another batch to run concurrently (see BoxFitter's pipelined mode).
+ * Needs H*W % 512 == 0 and a 16-byte aligned stack (LA3D_EINVAL otherwise: use la3d_mask_scan). */
+int la3d_mask_scan_thin(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
+                        uint32_t* chunk_counts, int ctas_per_sm, int stages, la3d_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * Mask statistics on the bit planes of la3d_mask_scan ("next" row f1 of the scope table): the
  * integer bookkeeping of analyze_mask (src/util.py:291-326), get_maximum_height
@@ -192,6 +200,9 @@ int la3d_fit_boxes_p2p(const float* depth, const uint8_t* masks, const double* K
                        int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed, uint32_t image_offset,
                        void* workspace, size_t workspace_bytes, void* const* peer_records, int n_peers, int rec_f64,
                        la3d_stream_t stream);
+int la3d_fit_scanned_p2p(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
+                         const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
+                         void* const* peer_records, int n_peers, int rec_f64, la3d_stream_t stream);
 int la3d_peer_barrier(uint32_t* const* flags, int rank, int world, uint32_t epoch, int* status, la3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------

@@ -730,6 +730,14 @@ extern "C" int la3d_fit_scanned(const float* depth, const void* prep, const uint
                                  rec_f64, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int la3d_fit_scanned_p2p(const float* depth, const void* prep, const uint32_t* bits,
+                                    const uint32_t* chunk_counts, const int32_t* ranks, int B, int I, int H, int W,
+                                    int method, int yaw_steps, void* const* peer_records, int n_peers, int rec_f64,
+                                    la3d_stream_t stream) {
+  return la3d::fit_scanned_multi(depth, prep, bits, chunk_counts, ranks, B, I, H, W, method, yaw_steps, peer_records,
+                                 n_peers, rec_f64, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int la3d_fit_points(const double* pts, const int64_t* offsets, const int32_t* sample_idx, const double* K,
                                const double* ground, int nboxes, int method, int yaw_steps, void* records,
                                int rec_f64, la3d_stream_t stream) {

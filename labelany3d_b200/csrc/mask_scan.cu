@@ -13,6 +13,8 @@
 // kPrep: the first `B` CTAs of the launch do not scan; they run the batch's
 // mask-independent, latency-bound preparation (MT19937 words, cameras, ground rotations;
 // prep.cuh), which so hides under the HBM-bound scan without a second stream.
+#include <cstdlib>
+
 #include "prep.cuh"
 
 namespace la3d {
@@ -100,6 +102,125 @@ __global__ void __launch_bounds__(kThreads, kPrep ? 8 : 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The "thin" form of the scan: a persistent kernel, a few CTAs per SM, whose memory-level
+// parallelism comes from the TMA unit instead of from resident threads.  One elected thread per CTA
+// streams the mask stack (a flat run of planes x H*W bytes when H*W is a multiple of 512) through a
+// ring of 16 KB shared-memory stages with cp.async.bulk + mbarrier; eight converter warps turn
+// each stage into bits and quarter counts, 32 bytes -> one finished bit word per lane.
+// Measured on B200 (config 2, tools/scan_variants.py): 3 CTAs/SM x 2 stages 5.90 TB/s, 2 x 3 5.51,
+// 1 x 4 3.2 TB/s (one CTA per SM is bound by the producer -> TMA -> mbarrier -> converter latency
+// chain, not by bytes in flight); the one-tile-per-CTA kernel above reaches 5.75 in the same loop.
+// It was built to run UNDER the sampler / fit of another batch (two streams): measured, both
+// kernels slow down by what the other takes (profiles/r1_pipeline_timeline.txt) - the SMs are
+// issue- and register-bound across scan + fit, so the step stays serial and this kernel is an
+// alternative entry point (la3d_mask_scan_thin), not the default.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStageBytes = 16384;                 // 32 chunks
+constexpr int kStageChunks = kStageBytes / kChunkPx;
+constexpr int kConvWarps = 8;
+constexpr int kThinThreads = 32 + kConvWarps * 32;
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    if (spins > (1u << 24)) __trap();            // a lost arrival must not hang the GPU
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+template <bool k01, int kStages>
+__global__ void __launch_bounds__(kThinThreads, 1)
+    mask_scan_thin_kernel(const uint8_t* __restrict__ masks, long long total_bytes, uint32_t* __restrict__ bits,
+                          uint32_t* __restrict__ chunk_counts) {
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n_tiles = (total_bytes + kStageBytes - 1) / kStageBytes;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConvWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages;
+        mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);        // a fresh barrier passes the first round
+        const long long off = t * kStageBytes;
+        const uint32_t bytes = (uint32_t)min((long long)kStageBytes, total_bytes - off);
+        mbar_expect_tx(&full[s], bytes);
+        tma_load_1d(ring + (size_t)s * kStageBytes, masks + off, bytes, &full[s]);
+      }
+    }
+    return;
+  }
+  const int cw = warp - 1;
+  int it = 0;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    const int s = it % kStages;
+    const long long off = t * kStageBytes;
+    const int n_chunks = (int)(min((long long)kStageBytes, total_bytes - off) / kChunkPx);
+    mbar_wait(&full[s], (it / kStages) & 1);
+    const unsigned char* stage = ring + (size_t)s * kStageBytes;
+    // a lane converts 32 consecutive bytes into one finished bit word: a warp covers two chunks
+    // (1024 pixels) per round and a stage takes two rounds per warp
+    constexpr int kRounds = kStageChunks / 2 / kConvWarps;
+    uint4 q[kRounds][2];
+#pragma unroll
+    for (int j = 0; j < kRounds; ++j) {
+      const int pair = cw + j * kConvWarps;                    // chunks 2*pair, 2*pair+1 of the stage
+      const bool live = 2 * pair + (lane >> 4) < n_chunks;
+      const uint4* src = reinterpret_cast<const uint4*>(stage + pair * (2 * kChunkPx) + lane * 32);
+      q[j][0] = live ? src[0] : make_uint4(0u, 0u, 0u, 0u);
+      q[j][1] = live ? src[1] : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);                    // the stage is in registers: hand it back
+    const long long chunk0 = t * kStageChunks;
+#pragma unroll
+    for (int j = 0; j < kRounds; ++j) {
+      const int pair = cw + j * kConvWarps;
+      if (2 * pair >= n_chunks) break;                         // warp-uniform
+      const bool live = 2 * pair + (lane >> 4) < n_chunks;
+      const uint32_t word = pack16<k01>(q[j][0]) | (pack16<k01>(q[j][1]) << 16);
+      // lanes 4q..4q+3 of a half-warp hold quarter q of its chunk (4 x 32 = 128 pixels: a byte never carries)
+      const uint32_t cnt = (uint32_t)__popc(word) << (8 * ((lane >> 2) & 3));
+      const uint32_t lo = __reduce_add_sync(0xffffffffu, lane < 16 ? cnt : 0u);
+      const uint32_t hi = __reduce_add_sync(0xffffffffu, lane < 16 ? 0u : cnt);
+      if (live) bits[(chunk0 + 2 * pair) * kChunkWords + lane] = word;
+      if (lane == 0) chunk_counts[chunk0 + 2 * pair] = lo;
+      if (lane == 16 && live) chunk_counts[chunk0 + 2 * pair + 1] = hi;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace la3d
 
@@ -109,6 +230,35 @@ extern "C" size_t la3d_chunks_per_plane(int H, int W) {
 extern "C" size_t la3d_words_per_plane(int H, int W) { return la3d_chunks_per_plane(H, W) * la3d::kChunkWords; }
 
 namespace la3d {
+static int g_scan_variant = -1;
+int scan_variant() {
+  if (g_scan_variant < 0) g_scan_variant = getenv("LA3D_SCAN_VARIANT") ? atoi(getenv("LA3D_SCAN_VARIANT")) : 0;
+  return g_scan_variant;
+}
+void set_scan_variant(int v) { g_scan_variant = v < 0 ? 0 : v; }
+
+// thin persistent form (see mask_scan_thin_kernel)
+static int launch_thin(const uint8_t* masks, int planes, int HW, int mask_is_01, uint32_t* bits, uint32_t* chunk_counts,
+                       int ctas_per_sm, int stages, cudaStream_t s) {
+  int dev = 0, sms = 0;
+  LA3D_CUDA(cudaGetDevice(&dev));
+  LA3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long total = (long long)planes * HW;
+  const long long n_tiles = (total + kStageBytes - 1) / kStageBytes;
+  const unsigned g = (unsigned)min((long long)sms * (ctas_per_sm > 0 ? ctas_per_sm : 1), n_tiles);
+#define THIN(B01, ST) do { \
+    const int smem = ST * kStageBytes; \
+    LA3D_CUDA(cudaFuncSetAttribute(mask_scan_thin_kernel<B01, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    mask_scan_thin_kernel<B01, ST><<<g, kThinThreads, smem, s>>>(masks, total, bits, chunk_counts); } while (0)
+  if (stages >= 6) { if (mask_is_01) THIN(true, 6); else THIN(false, 6); }
+  else if (stages >= 4) { if (mask_is_01) THIN(true, 4); else THIN(false, 4); }
+  else if (stages >= 3) { if (mask_is_01) THIN(true, 3); else THIN(false, 3); }
+  else { if (mask_is_01) THIN(true, 2); else THIN(false, 2); }
+#undef THIN
+  LA3D_CUDA(cudaGetLastError());
+  return LA3D_OK;
+}
+
 // prep == nullptr: the plain scan.  Otherwise prep->B extra CTAs at the front of the grid prepare the batch.
 int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
                      uint32_t* chunk_counts, const PrepArgs* prep, cudaStream_t s) {
@@ -121,6 +271,11 @@ int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is
   const long long ctas = (long long)tiles * planes + (prep ? prep->B : 0);
   LA3D_REQUIRE(ctas < (1ll << 31), "grid too large");
   const bool vec = (HW % 16 == 0) && aligned16(masks);
+  const int variant = scan_variant();
+  if (!prep && variant > 0 && HW % kChunkPx == 0 && aligned16(masks)) {
+    static const int per_sm = getenv("LA3D_SCAN_CTAS") ? atoi(getenv("LA3D_SCAN_CTAS")) : 3;
+    return launch_thin(masks, planes, HW, mask_is_01, bits, chunk_counts, per_sm, variant, s);
+  }
   dim3 grid((unsigned)ctas), block(kThreads);
   const PrepArgs pa = prep ? *prep : PrepArgs{};
 #define LAUNCH(B01, VEC, PREP) \
@@ -139,4 +294,15 @@ extern "C" int la3d_mask_scan(const uint8_t* masks, int planes, int H, int W, in
                               uint32_t* chunk_counts, la3d_stream_t stream) {
   return la3d::launch_mask_scan(masks, planes, H, W, mask_is_01, bits, chunk_counts, nullptr,
                                 static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int la3d_mask_scan_thin(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
+                                   uint32_t* chunk_counts, int ctas_per_sm, int stages, la3d_stream_t stream) {
+  using namespace la3d;
+  LA3D_REQUIRE(masks && bits && chunk_counts, "null pointer");
+  LA3D_REQUIRE(planes > 0 && H > 0 && W > 0, "non-positive shape");
+  LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
+  LA3D_REQUIRE((H * W) % kChunkPx == 0 && aligned16(masks), "the thin scan needs H*W to be a multiple of 512 and a 16-byte aligned stack");
+  LA3D_REQUIRE(ctas_per_sm >= 1 && ctas_per_sm <= 4 && stages >= 2, "1..4 CTAs per SM, at least 2 stages");
+  return launch_thin(masks, planes, H * W, mask_is_01, bits, chunk_counts, ctas_per_sm, stages, static_cast<cudaStream_t>(stream));
 }

@@ -91,8 +91,11 @@ def scan_layout(H, W):
     return int(lib.la3d_chunks_per_plane(H, W)), int(lib.la3d_words_per_plane(H, W))
 
 
-def mask_scan(masks):
+def mask_scan(masks, thin=None):
     """``masks[..., H, W]`` (bool / uint8) -> ``(bits[P, words] int32, chunk_counts[P, chunks] int32)``.
+
+    ``thin=(ctas_per_sm, stages)`` runs the persistent TMA-fed form (``la3d_mask_scan_thin``; needs
+    ``H*W % 512 == 0``) instead of the one-tile-per-CTA kernel; the results are identical.
 
     ``P`` = product of the leading dimensions.  Bit ``k`` of word ``w`` of a plane is
     pixel ``32 w + k`` in row-major order; a ``chunk_counts`` word packs the set-pixel counts
@@ -107,7 +110,11 @@ def mask_scan(masks):
     bits = torch.empty((planes, words), dtype=torch.int32, device=masks.device)
     cc = torch.empty((planes, chunks), dtype=torch.int32, device=masks.device)
     with torch.cuda.device(masks.device):
-        rc = lib.la3d_mask_scan(_ptr(m8), planes, H, W, is01, _ptr(bits), _ptr(cc), _stream())
+        if thin is None:
+            rc = lib.la3d_mask_scan(_ptr(m8), planes, H, W, is01, _ptr(bits), _ptr(cc), _stream())
+        else:
+            rc = lib.la3d_mask_scan_thin(_ptr(m8), planes, H, W, is01, _ptr(bits), _ptr(cc), int(thin[0]), int(thin[1]),
+                                         _stream())
     _lib.check(rc, "la3d_mask_scan")
     return bits, cc
 

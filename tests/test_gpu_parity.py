@@ -117,6 +117,22 @@ def test_mask_scan_exact(ops, shape, kind):
     np.testing.assert_array_equal(counts.cpu().numpy(), orc.mask_counts(m))
 
 
+@pytest.mark.parametrize("shape", [(2, 2, 96, 128), (1, 3, 16, 32), (3, 5, 64, 72), (1, 4, 480, 640)])
+@pytest.mark.parametrize("thin", [(1, 2), (2, 3), (3, 2), (2, 4), (1, 6)])
+def test_thin_tma_scan_equals_the_tile_scan(ops, shape, thin):
+    """The persistent TMA-fed scan (la3d_mask_scan_thin) is bit-identical to la3d_mask_scan, including a
+    partial last 16 KB stage and a stream shorter than the grid."""
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    m = torch.rand(shape, device="cuda", generator=g) < 0.3
+    m[0, 0, -1, :] = True
+    for masks in (m, (m.to(torch.uint8) * 7)):
+        bits, cc = ops.mask_scan(masks)
+        tbits, tcc = ops.mask_scan(masks, thin=thin)
+        assert torch.equal(bits, tbits) and torch.equal(cc, tcc)
+    with pytest.raises(Exception, match="multiple of 512"):
+        ops.mask_scan(torch.zeros((1, 1, 24, 32), dtype=torch.bool, device="cuda"), thin=(2, 2))
+
+
 def test_legacy_randint_stream(ops, golden):
     """The device MT19937 + masked rejection equals np.random.RandomState.randint, draw for draw."""
     H, W = 384, 385

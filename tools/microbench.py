@@ -67,6 +67,20 @@ def main():
         med, best = timeit(lambda: lib.la3d_fit_scanned(depth.data_ptr(), prep.data_ptr(), bits.data_ptr(), cc.data_ptr(),
                                                         ranks.data_ptr(), B, I, H, W, mid, steps, rec.data_ptr(), 1, st))
         out[f"fit_{name}_ms"] = med
+    # "next" rows: mask statistics, overlap, masked-median depth scale
+    stats = torch.empty((B * I, 8), dtype=torch.int32, device="cuda")
+    med, best = timeit(lambda: ops.mask_stats(bits, H, W, 10))
+    out["mask_stats_ms"] = med; out["mask_stats_GBs"] = bits.numel() * 4 / med / 1e6
+    fbits = bits.view(B, I, words)[:, 0].contiguous()
+    med, best = timeit(lambda: ops.mask_overlap(bits, fbits, H, W, group=I))
+    out["mask_overlap_ms"] = med; out["mask_overlap_GBs"] = bits.numel() * 4 * (1 + 1.0 / I) / med / 1e6
+    if px * I * 4 < 20e9:
+        render = (depth[:, None] / 2.5).expand(B, I, H, W).contiguous()
+        rb = torch.roll(bits, 1, 0).contiguous()
+        med, best = timeit(lambda: ops.depth_scale_median(depth, render, bits, rb, H, W), iters=5, warm=1)
+        n_ov, _ = ops.depth_scale_median(depth, render, bits, rb, H, W)
+        out["ratio_median_ms"] = med; out["ratio_median_overlap_px"] = int(n_ov.sum().item())
+        del render
     fit = ops.BoxFitter(B, I, H, W)
     for name, steps in (("pca", 0), ("sweep", c["yaw_steps"] or 36)):
         med, best = timeit(lambda: fit(depth, K, masks, ground, name, steps, seed=1234))

@@ -69,8 +69,7 @@ def main():
         ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         for r, n in zip(data, names):
             b = float(r[ir].replace(",", "")) * UNIT_SCALE[units[ir]] + float(r[iw].replace(",", "")) * UNIT_SCALE[units[iw]]
-            key = re.sub(r"<.*", "", n)
-            traffic.setdefault(key, []).append(b)
+            traffic.setdefault(n, []).append(b)
         with open(tj, "w") as f:
             json.dump({k: (v[0] if len(v) == 1 else v) for k, v in traffic.items()}, f, indent=1)
 

@@ -11,7 +11,7 @@ cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 c = dict(synth.CONFIGS[cfg])
 if len(sys.argv) > 2:
     c["B"] = int(sys.argv[2])
-which = sys.argv[3].split(",") if len(sys.argv) > 3 else ["lift", "scan", "sample", "pca", "sweep", "hull"]
+which = sys.argv[3].split(",") if len(sys.argv) > 3 else ["lift", "scan", "sample", "pca", "sweep", "hull", "step", "next"]
 B, I, H, W = c["B"], c["I"], c["H"], c["W"]
 depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=1234 + cfg, device="cuda")
 lib = _lib.load()
@@ -25,6 +25,7 @@ ranks = torch.empty((B, I, 500), dtype=torch.int32, device="cuda")
 rec = torch.empty((B, I, 64), dtype=torch.float64, device="cuda")
 o32 = torch.empty((B, H, W, 3), dtype=torch.float32, device="cuda")
 prep = torch.empty(lib.la3d_prep_bytes(B, I), dtype=torch.uint8, device="cuda")
+fitter = ops.BoxFitter(B, I, H, W, out_dtype=torch.float32)
 torch.cuda.synchronize()
 for _ in range(2):
     if "lift" in which:
@@ -36,5 +37,15 @@ for _ in range(2):
         if name in which:
             lib.la3d_fit_scanned(depth.data_ptr(), prep.data_ptr(), bits.data_ptr(), cc.data_ptr(),
                                  ranks.data_ptr(), B, I, H, W, mid, steps, rec.data_ptr(), 1, st)
+    if "step" in which:          # the one-call pipeline as bench.py runs it: scan (+ prep CTAs), sampler, fit
+        fitter(depth, K, masks, ground, "sweep", c["yaw_steps"] or 36, seed=1234)
+    if "next" in which:
+        lib.la3d_mask_scan_thin(m8.data_ptr(), B * I, H, W, 1, bits.data_ptr(), cc.data_ptr(), 3, 2, st)
+        ops.mask_stats(bits, H, W, 10)
+        ops.mask_overlap(bits, bits.view(B, I, words)[:, 0].contiguous(), H, W, group=I)
+        if B * I * H * W * 4 < 20e9:
+            render = (depth[:, None] / 2.5).expand(B, I, H, W).contiguous()
+            ops.depth_scale_median(depth, render, bits, torch.roll(bits, 1, 0).contiguous(), H, W)
+            del render
 torch.cuda.synchronize()
 print("done")
