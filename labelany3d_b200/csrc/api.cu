@@ -3,6 +3,7 @@
 // with its workspace.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include "prep.cuh"
 
 namespace la3d {
@@ -15,6 +16,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
+}
+
+// LA3D_PDL=1 launches the sampler and the fit as programmatic dependents (their launch latency and the
+// fit's prologue overlap the kernel before them).  Off by default: measured on B200 it costs 17 us per
+// step (204 vs 187 us) - the early-scheduled CTAs sit in griddepcontrol.wait on slots the scan's last
+// waves would have used.
+static bool pdl_enabled() {
+  static const bool v = getenv("LA3D_PDL") && atoi(getenv("LA3D_PDL")) != 0;
+  return v;
 }
 
 int cuda_fail(cudaError_t err, const char* what) {
@@ -83,10 +93,11 @@ static int fit_boxes_multi(const float* depth, const uint8_t* masks, const doubl
   const PrepArgs pa{K, ground, B, I, seed + image_offset, pv};
   int rc = launch_mask_scan(masks, B * I, H, W, mask_is_01, w.bits, w.chunk_counts, &pa, static_cast<cudaStream_t>(stream));
   if (rc) return rc;
-  rc = la3d_sample_ranks(w.chunk_counts, w.prep, B, I, H, W, w.counts, w.ranks, stream);
+  rc = launch_sample(w.chunk_counts, pv, B, I, (int)la3d_chunks_per_plane(H, W), w.counts, w.ranks,
+                     static_cast<cudaStream_t>(stream), pdl_enabled());
   if (rc) return rc;
   return fit_scanned_multi(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, records, n_out,
-                           rec_f64, static_cast<cudaStream_t>(stream));
+                           rec_f64, static_cast<cudaStream_t>(stream), pdl_enabled());
 }
 
 // Cross-GPU barrier over peer memory: rank r stores `epoch` into slot r of every peer's flag array

@@ -422,7 +422,12 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
     src_pts = a.pts + (size_t)o0 * 3;
   }
   __syncthreads();
-  if (kScanned) n_src = pref[a.chunks];        // = counts[box]
+  if (kScanned) {
+    n_src = pref[a.chunks];                    // = counts[box]
+    // up to here only outputs of the scan launch were read; the ranks come from the sampler, which may
+    // still be running when this kernel was launched as its programmatic dependent
+    pdl_wait();
+  }
 
   const bool subsample = n_src > LA3D_SUBSAMPLE;
   int status = LA3D_ST_OK;
@@ -675,7 +680,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   for (int f = tid; f < LA3D_REC; f += kThreads) put_record(a, (size_t)box * LA3D_REC + f, rec[f]);
 }
 
-int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s) {
+int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s, bool pdl = false) {
   a.n_areas = a.method == LA3D_METHOD_SWEEP ? (a.yaw_steps > 0 ? a.yaw_steps : 1)
             : a.method == LA3D_METHOD_CONVEX_HULL ? kMaxPts : 0;
   a.n_areas = (a.n_areas + 1) & ~1;                       // keep what follows 16-byte aligned
@@ -687,7 +692,7 @@ int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s) {
   }
   if (scanned) {
     if (dyn > 16 * 1024) LA3D_CUDA(cudaFuncSetAttribute(fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    fit_kernel<true><<<nboxes, kThreads, dyn, s>>>(a);
+    LA3D_CUDA(launch_pdl(fit_kernel<true>, dim3((unsigned)nboxes), dim3(kThreads), dyn, s, pdl, a));
   } else {
     if (dyn > 16 * 1024) LA3D_CUDA(cudaFuncSetAttribute(fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     fit_kernel<false><<<nboxes, kThreads, dyn, s>>>(a);
@@ -702,7 +707,7 @@ int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s) {
 namespace la3d {
 int fit_scanned_multi(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
                       const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
-                      void* const* records, int n_out, int rec_f64, cudaStream_t stream) {
+                      void* const* records, int n_out, int rec_f64, cudaStream_t stream, bool pdl) {
   LA3D_REQUIRE(depth && prep && bits && chunk_counts && ranks && records, "null pointer");
   LA3D_REQUIRE(n_out >= 1 && n_out <= LA3D_MAX_PEERS, "between 1 and LA3D_MAX_PEERS output buffers");
   LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
@@ -719,7 +724,7 @@ int fit_scanned_multi(const float* depth, const void* prep, const uint32_t* bits
     a.records[p] = records[p];
   }
   a.n_out = n_out;
-  return launch_fit(true, a, B * I, stream);
+  return launch_fit(true, a, B * I, stream, pdl);
 }
 }  // namespace la3d
 
@@ -727,7 +732,7 @@ extern "C" int la3d_fit_scanned(const float* depth, const void* prep, const uint
                                 const uint32_t* chunk_counts, const int32_t* ranks, int B, int I, int H, int W,
                                 int method, int yaw_steps, void* records, int rec_f64, la3d_stream_t stream) {
   return la3d::fit_scanned_multi(depth, prep, bits, chunk_counts, ranks, B, I, H, W, method, yaw_steps, &records, 1,
-                                 rec_f64, static_cast<cudaStream_t>(stream));
+                                 rec_f64, static_cast<cudaStream_t>(stream), false);
 }
 
 extern "C" int la3d_fit_scanned_p2p(const float* depth, const void* prep, const uint32_t* bits,
@@ -735,7 +740,7 @@ extern "C" int la3d_fit_scanned_p2p(const float* depth, const void* prep, const 
                                     int method, int yaw_steps, void* const* peer_records, int n_peers, int rec_f64,
                                     la3d_stream_t stream) {
   return la3d::fit_scanned_multi(depth, prep, bits, chunk_counts, ranks, B, I, H, W, method, yaw_steps, peer_records,
-                                 n_peers, rec_f64, static_cast<cudaStream_t>(stream));
+                                 n_peers, rec_f64, static_cast<cudaStream_t>(stream), false);
 }
 
 extern "C" int la3d_fit_points(const double* pts, const int64_t* offsets, const int32_t* sample_idx, const double* K,

@@ -61,6 +61,7 @@ template <bool k01, bool kVec, bool kPrep>
 __global__ void __launch_bounds__(kThreads, kPrep ? 8 : 1)
     mask_scan_kernel(const uint8_t* __restrict__ masks, int HW, int chunks_per_plane, int tiles_per_plane,
                      uint32_t* __restrict__ bits, uint32_t* __restrict__ chunk_counts, PrepArgs pa) {
+  pdl_trigger();          // the sampler (if launched as a programmatic dependent) may be scheduled early; it waits
   int bid = blockIdx.x;
   if (kPrep) {
     if (bid < pa.B) { prep_body<kThreads>(pa, bid); return; }     // CTA-uniform
@@ -120,38 +121,6 @@ constexpr int kStageBytes = 16384;                 // 32 chunks
 constexpr int kStageChunks = kStageBytes / kChunkPx;
 constexpr int kConvWarps = 8;
 constexpr int kThinThreads = 32 + kConvWarps * 32;
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
-  uint32_t done = 0;
-  for (uint32_t spins = 0; !done; ++spins) {
-    if (spins > (1u << 24)) __trap();            // a lost arrival must not hang the GPU
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
-               : "memory");
-}
 
 template <bool k01, int kStages>
 __global__ void __launch_bounds__(kThinThreads, 1)

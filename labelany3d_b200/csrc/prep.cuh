@@ -107,6 +107,6 @@ int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is
 
 int fit_scanned_multi(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
                       const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
-                      void* const* records, int n_out, int rec_f64, cudaStream_t stream);
+                      void* const* records, int n_out, int rec_f64, cudaStream_t stream, bool pdl = false);
 
 }  // namespace la3d

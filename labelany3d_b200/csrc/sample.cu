@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const uint32_t* __rest
                                                           int32_t* __restrict__ ranks) {
   __shared__ uint32_t mt[kMtN];               // generator state, only if the pre-generated words run out
   __shared__ int wtot[kWarps], end_pos;
-  extern __shared__ uint32_t dyn[];
+  extern __shared__ __align__(16) uint32_t dyn[];
   uint32_t* seg = dyn;                        // [seg_cap] staged words
   uint32_t* n_of = dyn + seg_cap;             // [I] set pixels per instance
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -55,18 +55,41 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const uint32_t* __rest
   const int nwords = pv.nblk * kMtN;          // pre-generated words of this image
   const uint32_t* words = pv.words + (size_t)b * nwords;
 
-  // stage the first segment while the counts are being totalled
+  // everything this kernel reads comes from the scan launch (counts, pre-generated words): wait for it,
+  // then let the fit kernel start its own prologue (which reads only what the scan launch wrote)
+  pdl_wait();
+  pdl_trigger();
+  // stage the first segment (one TMA bulk copy, signalled on an mbarrier) while the counts are totalled
+  __shared__ __align__(8) uint64_t seg_bar;
+  uint32_t seg_phase = 0;
   int seg_base = 0, seg_len = min(seg_cap, nwords);
-  for (int k = tid; k < seg_len; k += kThreads) seg[k] = __ldg(words + k);
+  if (tid == 0) {
+    mbar_init(&seg_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&seg_bar, (uint32_t)seg_len * 4u);
+    tma_load_1d(seg, words, (uint32_t)seg_len * 4u, &seg_bar);
+  }
   for (int i = warp; i < I; i += kWarps) {
     const uint32_t* cc = chunk_counts + (size_t)(b * I + i) * chunks;
     uint32_t n = 0;
+    if ((chunks & 3) == 0 && aligned16_dev(cc)) {   // 16-byte loads, all of a lane's in flight together
+      const uint4* cc4 = reinterpret_cast<const uint4*>(cc);
+#pragma unroll 8
+      for (int c = lane; c < chunks / 4; c += 32) {
+        const uint4 q = __ldg(cc4 + c);
+        n = __dp4a(q.x, 0x01010101u, n); n = __dp4a(q.y, 0x01010101u, n);
+        n = __dp4a(q.z, 0x01010101u, n); n = __dp4a(q.w, 0x01010101u, n);
+      }
+    } else {
 #pragma unroll 4
-    for (int c = lane; c < chunks; c += 32) n = __dp4a(__ldg(cc + c), 0x01010101u, n);   // sum of the 4 quarter bytes
+      for (int c = lane; c < chunks; c += 32) n = __dp4a(__ldg(cc + c), 0x01010101u, n);   // sum of the 4 quarter bytes
+    }
     n = __reduce_add_sync(kFull, n);
     if (lane == 0) { n_of[i] = n; counts[b * I + i] = (int32_t)n; }
   }
-  __syncthreads();
+  __syncthreads();                              // n_of and the barrier's initialisation are visible
+  mbar_wait(&seg_bar, seg_phase);
+  seg_phase ^= 1u;
 
   // every variable below is uniform across the CTA
   int pos = 0;        // next unread word of the image's stream
@@ -77,11 +100,18 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const uint32_t* __rest
   while (i < I) {
     if (pos >= seg_base + seg_len) {
       __syncthreads();                        // everyone is done with the old segment
-      seg_base = pos;
       if (pos < nwords) {
-        seg_len = min(seg_cap, nwords - pos);
-        for (int k = tid; k < seg_len; k += kThreads) seg[k] = __ldg(words + pos + k);
+        seg_base = pos & ~3;                    // 16-byte aligned source for the bulk copy
+        seg_len = min(seg_cap, nwords - seg_base);
+        if (tid == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy accesses of seg come first
+          mbar_expect_tx(&seg_bar, (uint32_t)seg_len * 4u);
+          tma_load_1d(seg, words + seg_base, (uint32_t)seg_len * 4u, &seg_bar);
+        }
+        mbar_wait(&seg_bar, seg_phase);
+        seg_phase ^= 1u;
       } else {
+        seg_base = pos;
         // out of pre-generated words (pos == nwords + a multiple of 624): continue the generator
         if (!have_state) {
           for (int k = tid; k < kMtN; k += kThreads) mt[k] = __ldg(pv.state + (size_t)b * kMtN + k);
@@ -175,13 +205,13 @@ PrepView prep_view(void* base, int B, int I, int nblk) {
 int prep_blocks(int I) { return auto_blocks(I); }
 
 int launch_sample(const uint32_t* chunk_counts, const PrepView& pv, int B, int I, int chunks, int32_t* counts,
-                  int32_t* ranks, cudaStream_t s) {
+                  int32_t* ranks, cudaStream_t s, bool pdl) {
   const int seg_cap = (pv.nblk < kSegBlocksMax ? pv.nblk : kSegBlocksMax) * kMtN;
   const size_t dyn = ((size_t)seg_cap + I) * 4;
   if (dyn > 48 * 1024)
     LA3D_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-  sample_kernel<<<(unsigned)B, kThreads, dyn, s>>>(chunk_counts, I, chunks, pv, seg_cap, counts, ranks);
-  LA3D_CUDA(cudaGetLastError());
+  LA3D_CUDA(launch_pdl(sample_kernel, dim3((unsigned)B), dim3(kThreads), dyn, s, pdl, chunk_counts, I, chunks, pv, seg_cap,
+                       counts, ranks));
   return LA3D_OK;
 }
 
