@@ -224,8 +224,18 @@ def main():
     B, I, H, W = w["B"], w["I"], w["H"], w["W"]
     # every rank owns B images of a B*world batch; inputs are generated where they live
     depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=SEED + 1000 * rank, device=dev)
-    fitter = (la_dist.ShardedBoxFitter(B * world, I, H, W, device=dev, out_dtype=torch.float32, collective=args.collective)
-              if world > 1 else None)
+    fitter = None
+    if world > 1:
+        try:
+            fitter = la_dist.ShardedBoxFitter(B * world, I, H, W, device=dev, out_dtype=torch.float32, collective=args.collective)
+            ok = torch.ones(1, device=dev)
+        except Exception as exc:  # noqa: BLE001  (no peer mapping on this box: say so and use the NCCL gather)
+            print(f"[bench] rank {rank}: peer-memory gather unavailable ({exc!r}); falling back to --collective nccl", file=sys.stderr)
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            args.collective = "nccl"
+            fitter = la_dist.ShardedBoxFitter(B * world, I, H, W, device=dev, out_dtype=torch.float32, collective="nccl")
     single = ops.BoxFitter(B, I, H, W, device=dev, out_dtype=torch.float32)
     boxes_per_step = B * I * world
 
