@@ -95,6 +95,78 @@ __global__ void __launch_bounds__(kThreads) mask_stats_kernel(const uint32_t* __
   }
 }
 
+// W a multiple of 128: a row is a whole number of 16-byte pieces, so a thread's piece (128 pixels)
+// lies in one row and the (row, piece) position advances without a division.
+__global__ void __launch_bounds__(kThreads) mask_stats_rows_kernel(const uint32_t* __restrict__ bits,
+                                                                   int words_per_plane, int H, int W, Bands bd,
+                                                                   int32_t* __restrict__ stats) {
+  extern __shared__ uint32_t row_any[];            // [ceil(H/32)] one bit per row
+  __shared__ int red[kWarps][5];
+  const int plane = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row_words = (H + 31) >> 5;
+  for (int k = tid; k < row_words; k += kThreads) row_any[k] = 0u;
+  __syncthreads();
+  const uint4* src = reinterpret_cast<const uint4*>(bits + (size_t)plane * words_per_plane);
+  const int q4 = W >> 7;                           // pieces per row
+  const int total = H * q4;
+  const int d_row = kThreads / q4, d_col = kThreads - d_row * q4;
+  int row = tid / q4, col = tid - row * q4;
+  int area = 0, top = 0, bottom = 0, left = 0, right = 0;
+  for (int idx = tid; idx < total; idx += kThreads) {
+    const uint4 v = __ldg(src + idx);
+    if (v.x | v.y | v.z | v.w) {
+      const int c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+      area += c;
+      if (row >= bd.t0 && row < bd.t1) top += c;
+      if (row >= bd.b0 && row < bd.b1) bottom += c;
+      const int u = col << 7;                      // first column of the piece
+      if (bd.l1 > u && bd.l0 < u + 128) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) left += pop_cols(w[k], 0, u + 32 * k, 32, bd.l0, bd.l1);
+      }
+      if (bd.r1 > u && bd.r0 < u + 128) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) right += pop_cols(w[k], 0, u + 32 * k, 32, bd.r0, bd.r1);
+      }
+      atomicOr(&row_any[row >> 5], 1u << (row & 31));
+    }
+    row += d_row; col += d_col;
+    if (col >= q4) { col -= q4; ++row; }
+  }
+  int v5[5] = {area, top, bottom, left, right};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) v5[k] = __reduce_add_sync(kFull, v5[k]);
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) red[warp][k] = v5[k];
+  __syncthreads();
+  if (warp == 0) {
+    int first = 0x7fffffff, last = -1, rows = 0;
+    for (int k = lane; k < row_words; k += 32) {
+      const uint32_t m = row_any[k];
+      if (m) {
+        rows += __popc(m);
+        first = min(first, (k << 5) + __ffs(m) - 1);
+        last = max(last, (k << 5) + 31 - __clz(m));
+      }
+    }
+    rows = __reduce_add_sync(kFull, rows);
+    first = __reduce_min_sync(kFull, first);
+    last = __reduce_max_sync(kFull, last);
+    if (lane < 5) {
+      int acc = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) acc += red[w][lane];
+      stats[(size_t)plane * 8 + lane] = acc;
+    }
+    if (lane == 5) stats[(size_t)plane * 8 + 5] = last < 0 ? -1 : first;
+    if (lane == 6) stats[(size_t)plane * 8 + 6] = last;
+    if (lane == 7) stats[(size_t)plane * 8 + 7] = rows;
+  }
+}
+
 // |a[p] & b[p / group]| per plane p: one warp per plane
 __global__ void __launch_bounds__(kThreads) mask_overlap_kernel(const uint32_t* __restrict__ a,
                                                                 const uint32_t* __restrict__ b, int planes, int group,
@@ -124,8 +196,12 @@ extern "C" int la3d_mask_stats(const uint32_t* bits, int planes, int H, int W, c
   const size_t dyn = (size_t)((H + 31) / 32) * 4;
   LA3D_REQUIRE(dyn <= 48 * 1024, "more than 393216 rows");
   Bands bd{bands[0], bands[1], bands[2], bands[3], bands[4], bands[5], bands[6], bands[7]};
-  mask_stats_kernel<<<(unsigned)planes, kThreads, dyn, static_cast<cudaStream_t>(stream)>>>(
-      bits, (int)la3d_words_per_plane(H, W), H, W, bd, stats);
+  if (W % 128 == 0 && W / 128 <= kThreads && aligned16(bits))
+    mask_stats_rows_kernel<<<(unsigned)planes, kThreads, dyn, static_cast<cudaStream_t>(stream)>>>(
+        bits, (int)la3d_words_per_plane(H, W), H, W, bd, stats);
+  else
+    mask_stats_kernel<<<(unsigned)planes, kThreads, dyn, static_cast<cudaStream_t>(stream)>>>(
+        bits, (int)la3d_words_per_plane(H, W), H, W, bd, stats);
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
 }
