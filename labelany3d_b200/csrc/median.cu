@@ -8,6 +8,9 @@
 // integer image of the float32 ratios); an even count averages the two middle values the way
 // np.median does for float32 (float32 add, then halve); any NaN ratio makes the median NaN
 // (np.median's NaN check).  Bit-exact with NumPy on float32 inputs.
+// The first pass walks the two bit planes once (16-byte loads), gathers the two depths of every
+// overlap pixel and parks the ratio keys in shared memory (up to 8192 of them);
+// the remaining passes then run on that list.  Larger overlaps re-walk the bit planes per pass.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -16,6 +19,7 @@ namespace la3d {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kCap = 8192;             // ratio keys kept in shared memory (32 KB)
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t order_key(float f) {
@@ -24,6 +28,22 @@ __device__ __forceinline__ uint32_t order_key(float f) {
 }
 __device__ __forceinline__ float key_value(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Warp-aggregated shared-memory counters: the ratios of one object sit in a narrow band, so most
+// lanes hit the same histogram bin; lanes with equal targets elect one to add for all of them.
+__device__ __forceinline__ void hist_add(int* hist, uint32_t digit) {
+  const unsigned act = __activemask();
+  const unsigned peers = __match_any_sync(act, digit);
+  if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[digit], __popc(peers));
+}
+__device__ __forceinline__ int take_slot(int* counter) {
+  const unsigned act = __activemask();
+  const int lane = threadIdx.x & 31, leader = __ffs(act) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(act));
+  base = __shfl_sync(act, base, leader);
+  return base + __popc(act & ((1u << lane) - 1u));
 }
 
 struct Plane {
@@ -38,19 +58,30 @@ struct Plane {
 // kFirst: also counts the overlap pixels and the NaN ratios.
 template <bool kFirst>
 __device__ __forceinline__ void histogram(const Plane& pl, uint32_t prefix, int shift, int* hist, int* n_total,
-                                          int* n_nan) {
+                                          int* n_nan, uint32_t* keys, int* n_keys) {
   int cnt = 0, nan = 0;
-  for (int w = threadIdx.x; w < pl.words; w += kThreads) {
-    uint32_t m = __ldg(pl.a + w) & __ldg(pl.b + w);
-    while (m) {
-      const int bit = __ffs(m) - 1;
-      m &= m - 1;
-      const int p = (w << 5) + bit;
-      const float r = __fdiv_rn(__ldg(pl.num + p), __ldg(pl.den + p));
-      if (kFirst) ++cnt;
-      if (r != r) { if (kFirst) ++nan; continue; }
-      const uint32_t key = order_key(r);
-      if (shift == 24 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 0xffu], 1);
+  const uint4* a4 = reinterpret_cast<const uint4*>(pl.a);
+  const uint4* b4 = reinterpret_cast<const uint4*>(pl.b);
+  for (int w4 = threadIdx.x; w4 < pl.words / 4; w4 += kThreads) {      // words is a multiple of 16
+    const uint4 x = __ldg(a4 + w4), y = __ldg(b4 + w4);
+    const uint32_t mm[4] = {x.x & y.x, x.y & y.y, x.z & y.z, x.w & y.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t m = mm[k];
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int p = (((w4 << 2) + k) << 5) + bit;
+        const float r = __fdiv_rn(__ldg(pl.num + p), __ldg(pl.den + p));
+        if (kFirst) ++cnt;
+        if (r != r) { if (kFirst) ++nan; continue; }
+        const uint32_t key = order_key(r);
+        if (kFirst) {
+          const int slot = take_slot(n_keys);
+          if (slot < kCap) keys[slot] = key;
+        }
+        if (shift == 24 || (key >> (shift + 8)) == (prefix >> (shift + 8))) hist_add(hist, (key >> shift) & 0xffu);
+      }
     }
   }
   if (kFirst) {
@@ -60,14 +91,23 @@ __device__ __forceinline__ void histogram(const Plane& pl, uint32_t prefix, int 
   }
 }
 
+// the same over the key list parked in shared memory by the first pass
+__device__ __forceinline__ void histogram_list(const uint32_t* keys, int n, uint32_t prefix, int shift, int* hist) {
+  for (int k = threadIdx.x; k < n; k += kThreads) {
+    const uint32_t key = keys[k];
+    if (shift == 24 || (key >> (shift + 8)) == (prefix >> (shift + 8))) hist_add(hist, (key >> shift) & 0xffu);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) ratio_median_kernel(const float* __restrict__ depth_map,
                                                                 const float* __restrict__ depth_render,
                                                                 const uint32_t* __restrict__ bits_a,
                                                                 const uint32_t* __restrict__ bits_b, int group, int HW,
                                                                 int words, int32_t* __restrict__ n_overlap,
                                                                 float* __restrict__ scale) {
+  extern __shared__ uint32_t keys[];                       // [kCap]
   __shared__ int hist[256];
-  __shared__ int s_total, s_nan, s_digit, s_below;
+  __shared__ int s_total, s_nan, s_digit, s_below, s_keys;
   const int plane = blockIdx.x, tid = threadIdx.x;
   Plane pl{bits_a + (size_t)plane * words, bits_b + (size_t)plane * words, depth_map + (size_t)(plane / group) * HW,
            depth_render + (size_t)plane * HW, words};
@@ -79,10 +119,11 @@ __global__ void __launch_bounds__(kThreads) ratio_median_kernel(const float* __r
     int k = 0;
     for (int shift = 24; shift >= 0; shift -= 8) {
       hist[tid] = 0;
-      if (tid == 0 && sel == 0 && shift == 24) { s_total = 0; s_nan = 0; }
+      if (tid == 0 && sel == 0 && shift == 24) { s_total = 0; s_nan = 0; s_keys = 0; }
       __syncthreads();
-      if (sel == 0 && shift == 24) histogram<true>(pl, prefix, shift, hist, &s_total, &s_nan);
-      else histogram<false>(pl, prefix, shift, hist, nullptr, nullptr);
+      if (sel == 0 && shift == 24) histogram<true>(pl, prefix, shift, hist, &s_total, &s_nan, keys, &s_keys);
+      else if (s_keys <= kCap) histogram_list(keys, s_keys, prefix, shift, hist);
+      else histogram<false>(pl, prefix, shift, hist, nullptr, nullptr, nullptr, nullptr);
       __syncthreads();
       if (sel == 0 && shift == 24) {
         n = s_total; n_nan = s_nan;
@@ -128,7 +169,9 @@ extern "C" int la3d_masked_ratio_median(const float* depth_map, const float* dep
   LA3D_REQUIRE(depth_map && depth_render && mask_bits && render_bits && n_overlap && scale, "null pointer");
   LA3D_REQUIRE(planes > 0 && group > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
-  ratio_median_kernel<<<(unsigned)planes, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  LA3D_REQUIRE(aligned16(mask_bits) && aligned16(render_bits), "bit planes must be 16-byte aligned");
+  LA3D_CUDA(cudaFuncSetAttribute(ratio_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * 4));
+  ratio_median_kernel<<<(unsigned)planes, kThreads, kCap * 4, static_cast<cudaStream_t>(stream)>>>(
       depth_map, depth_render, mask_bits, render_bits, group, H * W, (int)la3d_words_per_plane(H, W), n_overlap, scale);
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
