@@ -108,7 +108,8 @@ int la3d_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_0
 /* The same scan as a "thin" persistent kernel: ctas_per_sm CTAs per SM whose loads are issued by the
  * TMA unit (cp.async.bulk into a ring of `stages` 16 KB shared-memory stages, mbarrier-signalled),
  * so it reaches the same bandwidth with ~1/4 of the resident threads and leaves room on every SM for
- * the sampler / fit kernels of another batch to run concurrently (see BoxFitter's pipelined mode).
+ * the sampler / fit kernels of another batch to be resident beside it (DESIGN.md section 4 reports what
+ * that overlap measured).
  * Needs H*W % 512 == 0 and a 16-byte aligned stack (LA3D_EINVAL otherwise: use la3d_mask_scan). */
 int la3d_mask_scan_thin(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
                         uint32_t* chunk_counts, int ctas_per_sm, int stages, la3d_stream_t stream);

@@ -4,7 +4,7 @@
 // the reference) for a batch, in two kernels:
 //
 // prep_kernel (one CTA of 128 threads per image; depends on nothing the mask scan
-// produces, so la3d_fit_boxes runs it on a side stream UNDER the scan):
+// produces, so la3d_fit_boxes runs it as extra CTAs inside the scan's launch, see mask_scan.cu):
 //   - thread 0 seeds MT19937 the way np.random.seed(int) does (init_genrand, a
 //     serial 624-step recurrence) while thread 32 inverts the image's intrinsics and
 //     threads 64.. build the ground rotation of each instance (the scalar float64

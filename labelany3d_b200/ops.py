@@ -300,7 +300,7 @@ class BoxFitter:
 
     def capture(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0, out=None):
         """Record one call as a CUDA graph and return its ``replay()``: the kernels of a step (and
-        the stream fork / join of the pipelined path) are then launched by one ``cudaGraphLaunch``
+        the prep CTAs riding in the scan) are then launched by one ``cudaGraphLaunch``
         instead of a dozen driver calls.  The graph reads the SAME buffers on every replay: refill
         ``depth`` / ``K`` / ``masks`` / ``ground`` in place to process new data.  Returns
         ``(replay, records)``."""
@@ -308,7 +308,7 @@ class BoxFitter:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            for _ in range(2):                     # warm-up outside capture (lazy driver state, side streams)
+            for _ in range(2):                     # warm-up outside capture (lazy driver state)
                 self(depth, K, masks, ground, method, yaw_steps, seed, image_offset, out=rec)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)

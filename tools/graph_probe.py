@@ -1,4 +1,4 @@
-"""Step time of the one-call pipeline: eager launches vs CUDA-graph replay, for LA3D_PARTS set in the env."""
+"""Step time of the one-call pipeline: eager launches vs CUDA-graph replay."""
 import os
 import sys
 
@@ -32,4 +32,4 @@ replay, rec = fit.capture(depth, K, masks, ground, method, steps, seed=1234)
 graph = timeit(replay)
 torch.cuda.synchronize()
 same = torch.equal(torch.nan_to_num(rec), torch.nan_to_num(ref))
-print(f"parts={os.environ.get('LA3D_PARTS', 'auto')} {method}{steps}: eager {eager:.1f} us/step, graph {graph:.1f} us/step, identical={same}")
+print(f"{method}{steps}: eager {eager:.1f} us/step, graph {graph:.1f} us/step, identical={same}")

@@ -1,4 +1,6 @@
-"""Timeline of the pipelined fitter: when do scan / prepare / sample / fit of consecutive batches run?"""
+"""Two batches in flight on two streams (scan of batch k+1 under the sampler + fit of batch k): when do the
+kernels run and how long do they take when they share the SMs?  The experiment behind
+profiles/r1_pipeline_timeline.txt (argv: CTAs per SM and stages of the thin scan; 0 0 = the tile scan)."""
 import os
 import sys
 
