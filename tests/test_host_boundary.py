@@ -47,6 +47,43 @@ def test_library_exports_every_header_symbol():
     assert _lib.load().la3d_fit_workspace_bytes(256, 8, 480, 640) > 256 * 8 * 9600 * 4
 
 
+def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
+    """Argument checks come first in every entry point: null pointers / bad shapes return LA3D_EINVAL
+    with a message naming the function, without a CUDA call (so this runs on the CPU box)."""
+    lib = _lib.load()
+    EINVAL = -1
+    calls = {
+        "la3d_depth_lift": lambda: lib.la3d_depth_lift(None, None, 9, 0, None, None, 1, 4, 4, None, 0, None),
+        "la3d_mask_scan": lambda: lib.la3d_mask_scan(None, 1, 4, 4, 1, None, None, None),
+        "la3d_mask_scan_thin": lambda: lib.la3d_mask_scan_thin(None, 1, 16, 32, 1, None, None, 2, 2, None),
+        "la3d_mask_stats": lambda: lib.la3d_mask_stats(None, 1, 4, 4, None, None, None),
+        "la3d_mask_overlap": lambda: lib.la3d_mask_overlap(None, None, 1, 1, 4, 4, None, None),
+        "la3d_fit_prepare": lambda: lib.la3d_fit_prepare(None, None, 1, 1, 0, 0, None, 0, None),
+        "la3d_sample_ranks": lambda: lib.la3d_sample_ranks(None, None, 1, 1, 4, 4, None, None, None),
+        "la3d_fit_scanned": lambda: lib.la3d_fit_scanned(None, None, None, None, None, 1, 1, 4, 4, 0, 0, None, 0, None),
+        "la3d_fit_boxes": lambda: lib.la3d_fit_boxes(None, None, None, None, 1, 1, 4, 4, 1, 0, 0, 0, 0, None, 0, None, 0, None),
+        "la3d_fit_boxes_p2p": lambda: lib.la3d_fit_boxes_p2p(None, None, None, None, 1, 1, 4, 4, 1, 0, 0, 0, 0, None, 0, None, 1, 0, None),
+        "la3d_peer_barrier": lambda: lib.la3d_peer_barrier(None, 0, 1, 1, None, None),
+        "la3d_fit_points": lambda: lib.la3d_fit_points(None, None, None, None, None, 1, 0, 0, None, 0, None),
+        "la3d_project_points": lambda: lib.la3d_project_points(None, None, None, 1, None, None),
+        "la3d_iou_matrix": lambda: lib.la3d_iou_matrix(None, None, None, None, None, 1, None, None),
+        "la3d_box2d_from_corners": lambda: lib.la3d_box2d_from_corners(None, None, None, None, 1, None, None, None),
+        "la3d_masked_ratio_median": lambda: lib.la3d_masked_ratio_median(None, None, None, None, 1, 1, 4, 4, None, None, None),
+    }
+    for name, call in calls.items():
+        assert call() == EINVAL, name
+        assert b"null pointer" in lib.la3d_last_error(), (name, lib.la3d_last_error())
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.addressof(buf)
+    assert lib.la3d_mask_scan(p, 0, 4, 4, 1, p, p, None) == EINVAL and b"non-positive shape" in lib.la3d_last_error()
+    assert lib.la3d_mask_scan_thin(p, 1, 3, 5, 1, p, p, 2, 2, None) == EINVAL and b"multiple of 512" in lib.la3d_last_error()
+    assert lib.la3d_depth_lift(p, p, 5, 0, None, None, 1, 4, 4, p, 0, None) == EINVAL and b"k_stride" in lib.la3d_last_error()
+    assert lib.la3d_fit_scanned(p, p, p, p, p, 1, 1, 4, 4, 2, 0, p, 0, None) == EINVAL and b"yaw_steps" in lib.la3d_last_error()
+    assert lib.la3d_peer_barrier(ctypes.cast(p, ctypes.c_void_p), 3, 2, 1, None, None) == EINVAL
+    assert lib.la3d_prep_bytes(0, 4) == 0 and lib.la3d_fit_workspace_bytes(1, 0, 4, 4) == 0
+    assert lib.la3d_prep_bytes(256, 8) > 256 * 8 * 1024 * 4
+
+
 def test_record_layout_matches_header_and_oracle():
     from oracle import la3d_oracle as orc
     header = open(os.path.join(ROOT, "include", "la3d.h")).read()
