@@ -49,6 +49,26 @@ def iou2D(box1, box2):
     return m.cpu().numpy()[0, 0]
 
 
+# constant fields of an Omni3D annotation as the reference writes them (:254-262), in its key order
+_ANNO_HEAD = (("behind_camera", False), ("truncation", 0.0), ("visibility", 1), ("segmentation_pts", -1),
+              ("lidar_pts", -1), ("valid3D", True))
+_ANNO_COPIED = ("center_cam", "dimensions", "R_cam", "bbox3D_cam")     # taken over from the 3dbbox JSON entry
+
+
+def _annotation(src, name, cat_id, image_id, anno_id, dataset_id):
+    out = dict(_ANNO_HEAD)
+    out.update(category_name=name, category_id=cat_id, image_id=image_id, id=anno_id, dataset_id=dataset_id)
+    for key in _ANNO_COPIED:
+        out[key] = src.get(key)
+    out.update(bbox2D_proj=None, bbox2D_trunc=None, depth_error=-1)      # the two boxes are filled in after the GPU pass
+    return out
+
+
+def _image_entry(scene_name, split, K, W, H, image_id, dataset_id):
+    return dict(width=int(W), height=int(H), file_path=f"coco/images/{split}2017/{scene_name}.jpg", K=K.tolist(),
+                src_90_rotate=0, src_flagged=False, incomplete=False, id=image_id, dataset_id=dataset_id)
+
+
 def _match(iou):
     rows, cols = linear_sum_assignment(-iou)
     return [(i, j, iou[i, j]) for i, j in zip(rows, cols)]
@@ -72,62 +92,54 @@ def combine_coco_results(results_dir, split, output_path, bbox_filename="3dbbox.
     scene_ids = sorted([d for d in os.listdir(scene_dir) if os.path.isdir(os.path.join(scene_dir, d))])
     print(f"Found {len(scene_ids)} scenes in {scene_dir}")
 
-    dataset_id = 22 if split == "val" else 23
-    image_id = 1000000 if split == "val" else 2000000
-    annotation_id = 100000000 if split == "val" else 200000000
+    is_val = split == "val"
+    dataset_id = 22 if is_val else 23
+    image_id, annotation_id = (1000000, 100000000) if is_val else (2000000, 200000000)
 
-    # ---- pass 1 (host): read the scenes, apply the reference's skip rules, collect the numbers
-    images, scenes = [], []          # scenes: dict(annos=[...], bbox2d=list|None, first=index of its first box)
+    def warn(text):
+        print(f"Warning: {text}")
+
+    def load_json(path):
+        with open(path, "r") as f:
+            return json.load(f)
+
+    # ---- pass 1 (host): read the scenes, apply the reference's skip rules (:176-231), collect the numbers
+    images, scenes = [], []          # scenes: one dict per kept image (annos, 2D boxes, image size)
     corners, k_index, Ks, whs = [], [], [], []
     for scene_name in scene_ids:
-        scene_path = os.path.join(scene_dir, scene_name)
-        bbox_path = os.path.join(scene_path, bbox_filename)
-        cam_path = os.path.join(scene_path, "cam_params.json")
-        bbox2d_path = os.path.join(scene_path, "bboxes.json")
-        if not os.path.exists(bbox_path):
-            print(f"Warning: Missing {bbox_filename} in {scene_name}, skipping")
+        here = os.path.join(scene_dir, scene_name)
+        files = {key: os.path.join(here, name) for key, name in
+                 (("boxes3d", bbox_filename), ("camera", "cam_params.json"), ("boxes2d", "bboxes.json"))}
+        if not os.path.exists(files["boxes3d"]):
+            warn(f"Missing {bbox_filename} in {scene_name}, skipping")
             continue
-        if not os.path.exists(cam_path):
-            print(f"Warning: Missing cam_params.json in {scene_name}, skipping")
+        if not os.path.exists(files["camera"]):
+            warn(f"Missing cam_params.json in {scene_name}, skipping")
             continue
-        with open(cam_path, "r") as f:
-            cam_params = json.load(f)
-        K = np.array(cam_params["K"])
-        H, W = cam_params["H"], cam_params["W"]
-        image_dict = {"width": int(W), "height": int(H), "file_path": f"coco/images/{split}2017/{scene_name}.jpg",
-                      "K": K.tolist(), "src_90_rotate": 0, "src_flagged": False, "incomplete": False, "id": image_id,
-                      "dataset_id": dataset_id}
-        with open(bbox_path, "r") as f:
-            bbox_anno = json.load(f)
-        if len(bbox_anno) == 0:
-            print(f"Warning: Empty bbox in {scene_name}, skipping")
+        camera = load_json(files["camera"])
+        K, H, W = np.array(camera["K"]), camera["H"], camera["W"]
+        entries = load_json(files["boxes3d"])
+        if len(entries) == 0:
+            warn(f"Empty bbox in {scene_name}, skipping")
             continue
-        bbox2d_anno = None
-        if os.path.exists(bbox2d_path):
-            with open(bbox2d_path, "r") as f:
-                bbox2d_anno = json.load(f)
-        else:
-            print(f"Warning: Missing bboxes.json in {scene_name}, using projected bbox as bbox2D_tight")
-        images.append(image_dict)
+        tight = load_json(files["boxes2d"]) if os.path.exists(files["boxes2d"]) else None
+        if tight is None:
+            warn(f"Missing bboxes.json in {scene_name}, using projected bbox as bbox2D_tight")
+        images.append(_image_entry(scene_name, split, K, W, H, image_id, dataset_id))
         local = []
-        for anno in bbox_anno:
-            category_name = anno.get("category_name", "").replace("_", " ")
-            category_id = CATEGORY_NAME_TO_ID.get(category_name, -1)
-            if category_id == -1:
-                print(f"Warning: Unknown category '{category_name}' in {scene_name}, skipping")
+        for entry in entries:
+            name = entry.get("category_name", "").replace("_", " ")
+            cat_id = CATEGORY_NAME_TO_ID.get(name, -1)
+            if cat_id == -1:
+                warn(f"Unknown category '{name}' in {scene_name}, skipping")
                 continue
-            corners.append(np.array(anno["bbox3D_cam"], dtype=np.float64).reshape(8, 3))
+            corners.append(np.array(entry["bbox3D_cam"], dtype=np.float64).reshape(8, 3))
             k_index.append(len(Ks))
-            local.append({"behind_camera": False, "truncation": 0.0, "visibility": 1, "segmentation_pts": -1,
-                          "lidar_pts": -1, "valid3D": True, "category_name": category_name, "category_id": category_id,
-                          "image_id": image_id, "id": annotation_id, "dataset_id": dataset_id,
-                          "center_cam": anno.get("center_cam"), "dimensions": anno.get("dimensions"),
-                          "R_cam": anno.get("R_cam"), "bbox3D_cam": anno.get("bbox3D_cam"),
-                          "bbox2D_proj": None, "bbox2D_trunc": None, "depth_error": -1})
+            local.append(_annotation(entry, name, cat_id, image_id, annotation_id, dataset_id))
             annotation_id += 1
         Ks.append(K.astype(np.float64).reshape(3, 3))
         whs.append([float(W), float(H)])
-        scenes.append({"annos": local, "bbox2d": bbox2d_anno, "W": W, "H": H, "match": False})
+        scenes.append({"annos": local, "bbox2d": tight, "W": W, "H": H, "match": False})
         image_id += 1
 
     # ---- pass 2 (GPU): every box of every scene in one launch, every cost matrix in another
@@ -182,13 +194,17 @@ def combine_coco_results(results_dir, split, output_path, bbox_filename="3dbbox.
     print(f"Saved {len(images)} images, {len(annotations)} annotations to {output_path}")
 
 
+def main(argv=None):
+    """Same command line as the reference script (:314-326)."""
+    cli = argparse.ArgumentParser(description="Combine COCO 3D bbox results into Omni3D format")
+    cli.add_argument("--split", default="val", choices=["train", "val"], type=str, help="Dataset split")
+    cli.add_argument("--results_dir", default="../experimental_results/COCO", type=str, help="Results directory")
+    cli.add_argument("--output", default=None, type=str, help="Output JSON path")
+    cli.add_argument("--bbox_file", default="3dbbox.json", type=str, help="3D bbox JSON filename")
+    opts = cli.parse_args(argv)
+    target = opts.output if opts.output is not None else os.path.join(opts.results_dir, f"COCO3D_{opts.split}.json")
+    combine_coco_results(opts.results_dir, opts.split, target, opts.bbox_file)
+
+
 if __name__ == "__main__":
-    parser = argparse.ArgumentParser(description="Combine COCO 3D bbox results into Omni3D format")
-    parser.add_argument("--split", type=str, default="val", choices=["train", "val"], help="Dataset split")
-    parser.add_argument("--results_dir", type=str, default="../experimental_results/COCO", help="Results directory")
-    parser.add_argument("--output", type=str, default=None, help="Output JSON path")
-    parser.add_argument("--bbox_file", type=str, default="3dbbox.json", help="3D bbox JSON filename")
-    args = parser.parse_args()
-    if args.output is None:
-        args.output = os.path.join(args.results_dir, f"COCO3D_{args.split}.json")
-    combine_coco_results(args.results_dir, args.split, args.output, args.bbox_file)
+    main()
