@@ -25,8 +25,10 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def _need_cuda(name, t, dtype=None):
-    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+def _need_cuda(name, t, dtype=None, pinned_ok=False):
+    """``pinned_ok``: page-locked host memory is accepted too (the kernels read it in place over PCIe
+    through unified addressing; the arithmetic still runs on the GPU)."""
+    if not isinstance(t, torch.Tensor) or not (t.is_cuda or (pinned_ok and t.is_pinned())):
         raise TypeError(f"{name} must be a CUDA tensor (this path has no CPU implementation)")
     if dtype is not None and t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
@@ -249,7 +251,8 @@ class BoxFitter:
         peer-mapped record buffers; the fit kernel then writes every record to all of them
         (``la3d_fit_boxes_p2p``) instead of to ``out``."""
         B, I, H, W = self.shape
-        depth = _need_cuda("depth", depth, torch.float32)
+        # the fit gathers only 500 depth values per box, so the depth maps may stay in pinned host memory
+        depth = _need_cuda("depth", depth, torch.float32, pinned_ok=True)
         K = _need_cuda("K", K, torch.float64)
         masks = _need_cuda("masks", masks)
         if tuple(depth.shape) != (B, H, W) or tuple(masks.shape) != (B, I, H, W) or tuple(K.shape) != (B, 3, 3):
@@ -332,6 +335,63 @@ class BoxFitter:
         prep_bytes = int(self.lib.la3d_prep_bytes(B, I))
         assert up(o_prep + prep_bytes) == self.ws_bytes
         return base, base + o_cc, base + o_counts, base + o_ranks, base + o_prep, prep_bytes
+
+
+class HostBoxFitter:
+    """Boxes straight from page-locked HOST buffers: the end-to-end form of the path.
+
+    Per call the mask stack, intrinsics and ground normals are copied to the device on a copy stream
+    into one of two buffer sets, so the copy of batch k+1 overlaps the kernels of batch k; the depth
+    maps are NOT copied: the fit reads 500 depth values per box, which the kernel gathers in place
+    from the pinned host buffer over PCIe (a third of the input bytes never cross the bus); the records
+    are copied back into a pinned host tensor.  ``fitter`` is a ``BoxFitter`` or a
+    ``dist.ShardedBoxFitter`` (anything with their call signature).  Everything is asynchronous: a
+    call returns an event that fires when its records have landed in ``out_host``; the host inputs
+    of a call must stay untouched until then.
+    """
+
+    def __init__(self, fitter, B, I, H, W, device="cuda", depth_in_place=True):
+        self.fitter = fitter
+        self.device = torch.device(device)
+        self.depth_in_place = bool(depth_in_place)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        mk = lambda shape, dt: [torch.empty(shape, dtype=dt, device=self.device) for _ in range(2)]  # noqa: E731
+        self.d_K, self.d_masks = mk((B, 3, 3), torch.float64), mk((B, I, H, W), torch.bool)
+        self.d_ground = mk((B, I, 3), torch.float64)
+        self.d_depth = None if self.depth_in_place else mk((B, H, W), torch.float32)
+        self.ev_ready = [torch.cuda.Event() for _ in range(2)]
+        self.ev_free = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+
+    def h2d_bytes(self, B, I, H, W):
+        """Bytes that cross the bus host->device per call (gathered depth counted as 32-byte sectors)."""
+        copied = B * 72 + B * I * H * W + B * I * 24
+        return copied + (B * I * SUBSAMPLE * 32 if self.depth_in_place else B * H * W * 4)
+
+    def __call__(self, depth, K, masks, ground, out_host, method="pca", yaw_steps=0, seed=0):
+        for name, t in (("depth", depth), ("K", K), ("masks", masks), ("ground", ground), ("out_host", out_host)):
+            if t is not None and not (isinstance(t, torch.Tensor) and t.is_pinned()):
+                raise TypeError(f"{name} must be a pinned host tensor")
+        s = self.k & 1
+        self.k += 1
+        cur = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_event(self.ev_free[s])          # the kernels of batch k-2 are done with this set
+        with torch.cuda.stream(self.copy_stream):
+            self.d_K[s].copy_(K, non_blocking=True)
+            self.d_masks[s].copy_(masks, non_blocking=True)
+            if ground is not None:
+                self.d_ground[s].copy_(ground, non_blocking=True)
+            if not self.depth_in_place:
+                self.d_depth[s].copy_(depth, non_blocking=True)
+            self.ev_ready[s].record(self.copy_stream)
+        cur.wait_event(self.ev_ready[s])
+        rec = self.fitter(depth if self.depth_in_place else self.d_depth[s], self.d_K[s], self.d_masks[s],
+                          None if ground is None else self.d_ground[s], method, yaw_steps, seed=seed)
+        out_host.copy_(rec, non_blocking=True)
+        self.ev_free[s].record(cur)
+        done = torch.cuda.Event()
+        done.record(cur)
+        return done
 
 
 def fit_boxes(depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0,

@@ -390,3 +390,26 @@ def test_full_size_other_configs(ops, cfg):
     want = orc.fit_boxes(depth[sl].cpu().numpy(), K[sl].cpu().numpy(), masks[sl].cpu().numpy(),
                          ground[sl].cpu().numpy(), method, steps, seed=1234, image_offset=B - 1, impl="closed")
     check_record(r[sl], want, TOL_F64 * (10 if method == "pca" else 1), skip=(orc.O_NVALID,))
+
+
+@pytest.mark.parametrize("in_place", [True, False])
+def test_host_box_fitter_equals_the_device_path(ops, in_place):
+    """Pinned host buffers in, pinned host records out (copy of batch k+1 under the kernels of batch k;
+    depth gathered in place from host memory or copied): the same records as the device-resident path."""
+    from labelany3d_b200 import synth
+    B, I, H, W = 4, 3, 96, 128
+    fit = ops.BoxFitter(B, I, H, W)
+    host = ops.HostBoxFitter(fit, B, I, H, W, depth_in_place=in_place)
+    outs, wants, events = [], [], []
+    for step in range(4):                                   # more batches than buffer sets
+        depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=40 + step, device="cuda", area=(0.05, 0.3))
+        wants.append(ops.fit_boxes(depth, K, masks, ground, "sweep", 36, seed=step).cpu().numpy())
+        h = [t.cpu().pin_memory() for t in (depth, K, masks, ground)]
+        out = torch.empty((B, I, 64), dtype=torch.float64).pin_memory()
+        events.append((host(h[0], h[1], h[2], h[3], out, "sweep", 36, seed=step), h))
+        outs.append(out)
+    for (ev, _), out, want in zip(events, outs, wants):
+        ev.synchronize()
+        np.testing.assert_array_equal(out.numpy(), want)
+    with pytest.raises(TypeError, match="pinned"):
+        host(torch.zeros((B, H, W)), events[0][1][1], events[0][1][2], None, outs[0])
