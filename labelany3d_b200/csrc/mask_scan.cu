@@ -10,9 +10,9 @@
 // A warp converts 4 consecutive 512-pixel chunks per step: 4 independent
 // 16-byte loads per lane are in flight before the first is used.
 //
-// kPrep: the first `B` CTAs of the launch do not scan; they run the batch's
-// mask-independent, latency-bound preparation (MT19937 words, cameras, ground rotations;
-// prep.cuh), which so hides under the HBM-bound scan without a second stream.
+// kPrep: the first ceil(B/8) CTAs of the launch do not scan; each of their warps runs one
+// image's mask-independent, latency-bound preparation (MT19937 words, cameras, ground
+// rotations; prep.cuh), which so hides under the HBM-bound scan without a second stream.
 #include <cstdlib>
 
 #include "prep.cuh"
@@ -64,8 +64,9 @@ __global__ void __launch_bounds__(kThreads, kPrep ? 8 : 1)
   pdl_trigger();          // the sampler (if launched as a programmatic dependent) may be scheduled early; it waits
   int bid = blockIdx.x;
   if (kPrep) {
-    if (bid < pa.B) { prep_body<kThreads>(pa, bid); return; }     // CTA-uniform
-    bid -= pa.B;
+    const int prep_ctas = (pa.B + kWarps - 1) / kWarps;           // one warp per image
+    if (bid < prep_ctas) { prep_body<kThreads>(pa, bid * kWarps); return; }     // CTA-uniform
+    bid -= prep_ctas;
   }
   const int plane = bid / tiles_per_plane;
   const int tile = bid - plane * tiles_per_plane;
@@ -237,7 +238,7 @@ int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is
   const int HW = H * W;
   const int chunks = (int)la3d_chunks_per_plane(H, W);
   const int tiles = (chunks + kTileChunks - 1) / kTileChunks;
-  const long long ctas = (long long)tiles * planes + (prep ? prep->B : 0);
+  const long long ctas = (long long)tiles * planes + (prep ? (prep->B + kWarps - 1) / kWarps : 0);
   LA3D_REQUIRE(ctas < (1ll << 31), "grid too large");
   const bool vec = (HW % 16 == 0) && aligned16(masks);
   const int variant = scan_variant();

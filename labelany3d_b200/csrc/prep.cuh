@@ -65,22 +65,59 @@ __device__ __forceinline__ void mt_next_block(uint32_t* mt, uint32_t* out) {
   for (int k = tid; k < kMtN; k += kT) out[k] = temper(mt[k]);
 }
 
-// One CTA of kT threads prepares image b: thread 0 seeds MT19937 (init_genrand) while thread 32
-// inverts the intrinsics and threads 64.. build the ground rotations; then the whole CTA
-// generates the image's first pv.nblk blocks of tempered words and saves the state.
+// The same for ONE WARP (no block barrier): 227 words per phase = 8 rounds of 32 lanes.
+__device__ __forceinline__ void mt_next_block_warp(uint32_t* mt, uint32_t* out) {
+  const int lane = threadIdx.x & 31;
+  constexpr int kSpan = kMtN - kMtM;                 // 227
+  constexpr int kIter = (kSpan + 31) / 32;
+#pragma unroll
+  for (int phase = 0; phase < 3; ++phase) {
+    const int lo = phase * kSpan, hi = min(lo + kSpan, kMtN - 1);
+    uint32_t val[kIter];
+#pragma unroll
+    for (int j = 0; j < kIter; ++j) {
+      const int kk = lo + lane + j * 32;
+      val[j] = 0;
+      if (kk < hi) {
+        const uint32_t far = (kk < kSpan) ? mt[kk + kMtM] : mt[kk - kSpan];
+        val[j] = far ^ twist(mt[kk], mt[kk + 1]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kIter; ++j) {
+      const int kk = lo + lane + j * 32;
+      if (kk < hi) mt[kk] = val[j];
+    }
+    __syncwarp();
+  }
+  if (lane == 0) mt[kMtN - 1] = mt[kMtM - 1] ^ twist(mt[kMtN - 1], mt[0]);
+  __syncwarp();
+  for (int k = lane; k < kMtN; k += 32) out[k] = temper(mt[k]);
+  __syncwarp();
+}
+
+// One WARP prepares one image (a CTA of kT threads prepares kT/32 consecutive images; `first` is the
+// CTA's first image): lane 0 seeds MT19937 (init_genrand), lane 1 inverts the intrinsics, the other
+// lanes build the ground rotations; then the warp generates the image's first pv.nblk blocks of
+// tempered words and saves the state.  Latency-bound on purpose: these warps ride in the launch of
+// the HBM-bound mask scan and should take as few of its slots as possible.
 template <int kT>
-__device__ __forceinline__ void prep_body(const PrepArgs& pa, int b) {
-  __shared__ uint32_t mt[kMtN];
-  const int tid = threadIdx.x;
+__device__ __forceinline__ void prep_body(const PrepArgs& pa, int first) {
+  __shared__ uint32_t mt_all[kT / 32][kMtN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = first + warp;
+  if (b >= pa.B) return;                               // warp-uniform; no block barrier below
+  uint32_t* mt = mt_all[warp];
   const PrepView& pv = pa.pv;
-  if (tid == 0) {
+  if (lane == 0) {
     uint32_t s = pa.seed0 + (uint32_t)b;       // mod 2^32, as np.random.seed requires
 #pragma unroll 8
     for (int i = 0; i < kMtN; ++i) {
       mt[i] = s;
       s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
     }
-  } else if (tid == 32) {
+  } else if (lane == 1) {
     PrepCamera* cam = pv.cams + b;
     double Km[9], Kinv[9];
 #pragma unroll
@@ -88,18 +125,18 @@ __device__ __forceinline__ void prep_body(const PrepArgs& pa, int b) {
     invert3x3(Km, Kinv);
 #pragma unroll
     for (int i = 0; i < 9; ++i) { cam->K[i] = Km[i]; cam->Kinv[i] = Kinv[i]; }
-  } else if (tid >= 64) {
-    for (int i = tid - 64; i < pa.I; i += kT - 64) {
+  } else {
+    for (int i = lane - 2; i < pa.I; i += 30) {
       double Rg[9];
       ground_rotation(pa.ground ? pa.ground + ((size_t)b * pa.I + i) * 3 : nullptr, Rg);
 #pragma unroll
       for (int k = 0; k < 9; ++k) pv.Rg[((size_t)b * pa.I + i) * 9 + k] = Rg[k];
     }
   }
-  __syncthreads();
+  __syncwarp();
   uint32_t* words = pv.words + (size_t)b * pv.nblk * kMtN;
-  for (int blk = 0; blk < pv.nblk; ++blk) mt_next_block<kT>(mt, words + (size_t)blk * kMtN);
-  for (int k = tid; k < kMtN; k += kT) pv.state[(size_t)b * kMtN + k] = mt[k];
+  for (int blk = 0; blk < pv.nblk; ++blk) mt_next_block_warp(mt, words + (size_t)blk * kMtN);
+  for (int k = lane; k < kMtN; k += 32) pv.state[(size_t)b * kMtN + k] = mt[k];
 }
 
 int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,

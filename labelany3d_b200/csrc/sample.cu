@@ -3,16 +3,16 @@
 // Replaces `rand_ind = np.random.randint(0, N, 500)` (src/util_3dbox.py:123-125 of
 // the reference) for a batch, in two kernels:
 //
-// prep_kernel (one CTA of 128 threads per image; depends on nothing the mask scan
-// produces, so la3d_fit_boxes runs it as extra CTAs inside the scan's launch, see mask_scan.cu):
-//   - thread 0 seeds MT19937 the way np.random.seed(int) does (init_genrand, a
-//     serial 624-step recurrence) while thread 32 inverts the image's intrinsics and
-//     threads 64.. build the ground rotation of each instance (the scalar float64
-//     work the fit kernel would otherwise repeat per box);
-//   - the CTA then advances the generator 624 words at a time (the twist has
-//     dependency distance 227, so a block is three data-parallel phases) and writes the
-//     TEMPERED words of the first `nblk` blocks to global memory, followed by the raw
-//     state, from which the consumer can continue should it ever run out of words.
+// prep (prep.cuh; one WARP per image; depends on nothing the mask scan produces, so
+// la3d_fit_boxes runs it as a few extra CTAs inside the scan's launch, see mask_scan.cu):
+//   - lane 0 seeds MT19937 the way np.random.seed(int) does (init_genrand, a serial 624-step
+//     recurrence), lane 1 inverts the image's intrinsics, the other lanes build the ground
+//     rotation of each instance (the scalar float64 work the fit kernel would otherwise repeat
+//     per box);
+//   - the warp then advances the generator 624 words at a time (the twist has dependency
+//     distance 227, so a block is three data-parallel phases) and writes the TEMPERED words of
+//     the first `nblk` blocks to global memory, followed by the raw state, from which the
+//     consumer can continue should it ever run out of words.
 //
 // sample_kernel (one CTA of 256 threads per image, after the scan):
 //   - totals the per-chunk quarter counts of the image's planes (N per instance);
@@ -40,7 +40,9 @@ constexpr unsigned kFull = 0xffffffffu;
 
 int g_mt_blocks = 0;                       // 0 = automatic (la3d_set_mt_blocks)
 
-__global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepArgs pa) { prep_body<kPrepThreads>(pa, blockIdx.x); }
+__global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepArgs pa) {
+  prep_body<kPrepThreads>(pa, blockIdx.x * (kPrepThreads / 32));
+}
 
 __global__ void __launch_bounds__(kThreads) sample_kernel(const uint32_t* __restrict__ chunk_counts, int I, int chunks,
                                                           PrepView pv, int seg_cap, int32_t* __restrict__ counts,
@@ -236,7 +238,7 @@ extern "C" int la3d_fit_prepare(const double* K, const double* ground, int B, in
     set_error("la3d_fit_prepare: buffer of %zu bytes, %zu needed", prep_bytes, pv.bytes);
     return LA3D_ENOMEM;
   }
-  prep_kernel<<<(unsigned)B, kPrepThreads, 0, static_cast<cudaStream_t>(stream)>>>(PrepArgs{K, ground, B, I, seed + image_offset, pv});
+  prep_kernel<<<(unsigned)((B + kPrepThreads / 32 - 1) / (kPrepThreads / 32)), kPrepThreads, 0, static_cast<cudaStream_t>(stream)>>>(PrepArgs{K, ground, B, I, seed + image_offset, pv});
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
 }
