@@ -244,7 +244,9 @@ def main():
 
     def step(events=None):
         if fitter is not None and events is None:
-            return fitter(depth, K, masks, ground, w["method"], w["yaw_steps"], seed=1234)
+            # wait=False: the peer barrier of step k runs on a side stream and gates only the fit of step k+1;
+            # the timed region ends with wait_gathered() + a device synchronisation, so every gather is inside it
+            return fitter(depth, K, masks, ground, w["method"], w["yaw_steps"], seed=1234, wait=False)
         # per-kernel timing (events) is a local matter: this rank's block without the gather
         return single(depth, K, masks, ground, w["method"], w["yaw_steps"], seed=1234, image_offset=B * rank, events=events)
 
@@ -265,6 +267,8 @@ def main():
     t_beg.record()
     for k in range(args.steps):
         step()
+    if fitter is not None:
+        fitter.wait_gathered()
     t_end.record()
     fence()
     if clocks:

@@ -195,12 +195,16 @@ int la3d_fit_boxes(const float* depth, const uint8_t* masks, const double* K, co
  *   flags:        HOST array of `world` device pointers; flags[p] = rank p's array of >= world uint32
  *                 (peer-mapped, zero-initialised once); epoch must grow by one per barrier
  *   status:       nullable device int, set to 1 if a peer did not arrive within ~2 s
+ *   wait_before_fit: nullable cudaEvent_t; `stream` waits for it between the sampler and the fit
+ *                 kernel.  Pass the event recorded after the PREVIOUS step's la3d_peer_barrier (run on
+ *                 another stream): the peer buffers are then known to be free again exactly when the
+ *                 fit starts writing them, and the barrier hides under this step's scan and sampler.
  * ------------------------------------------------------------------------- */
 #define LA3D_MAX_PEERS 8
 int la3d_fit_boxes_p2p(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
                        int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed, uint32_t image_offset,
                        void* workspace, size_t workspace_bytes, void* const* peer_records, int n_peers, int rec_f64,
-                       la3d_stream_t stream);
+                       void* wait_before_fit, la3d_stream_t stream);
 int la3d_fit_scanned_p2p(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
                          const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
                          void* const* peer_records, int n_peers, int rec_f64, la3d_stream_t stream);

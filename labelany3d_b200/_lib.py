@@ -30,7 +30,7 @@ SIGNATURES = {
     "la3d_fit_scanned": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "la3d_fit_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "la3d_fit_boxes": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _i, _vp]),
-    "la3d_fit_boxes_p2p": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _i, _i, _vp]),
+    "la3d_fit_boxes_p2p": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _i, _i, _vp, _vp]),
     "la3d_fit_scanned_p2p": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "la3d_peer_barrier": (_i, [_vp, _i, _i, _u32, _vp, _vp]),
     "la3d_fit_points": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),

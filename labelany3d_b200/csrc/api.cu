@@ -77,7 +77,7 @@ namespace la3d {
 static int fit_boxes_multi(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
                            int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
                            uint32_t image_offset, void* workspace, size_t workspace_bytes, void* const* records,
-                           int n_out, int rec_f64, la3d_stream_t stream) {
+                           int n_out, int rec_f64, void* wait_before_fit, la3d_stream_t stream) {
   LA3D_REQUIRE(depth && masks && K && workspace && records, "null pointer");
   LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
@@ -96,8 +96,13 @@ static int fit_boxes_multi(const float* depth, const uint8_t* masks, const doubl
   rc = launch_sample(w.chunk_counts, pv, B, I, (int)la3d_chunks_per_plane(H, W), w.counts, w.ranks,
                      static_cast<cudaStream_t>(stream), pdl_enabled());
   if (rc) return rc;
+  // multi-GPU: the records go into peer buffers that may still be read from the step before last;
+  // the caller's event (the peer barrier of the previous step) gates only the fit, so that barrier
+  // and the skew between ranks hide under this step's scan and sampler
+  if (wait_before_fit)
+    LA3D_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(wait_before_fit), 0));
   return fit_scanned_multi(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, records, n_out,
-                           rec_f64, static_cast<cudaStream_t>(stream), pdl_enabled());
+                           rec_f64, static_cast<cudaStream_t>(stream), pdl_enabled() && !wait_before_fit);
 }
 
 // Cross-GPU barrier over peer memory: rank r stores `epoch` into slot r of every peer's flag array
@@ -126,15 +131,16 @@ extern "C" int la3d_fit_boxes(const float* depth, const uint8_t* masks, const do
                               uint32_t image_offset, void* workspace, size_t workspace_bytes, void* records,
                               int rec_f64, la3d_stream_t stream) {
   return la3d::fit_boxes_multi(depth, masks, K, ground, B, I, H, W, mask_is_01, method, yaw_steps, seed, image_offset,
-                               workspace, workspace_bytes, &records, 1, rec_f64, stream);
+                               workspace, workspace_bytes, &records, 1, rec_f64, nullptr, stream);
 }
 
 extern "C" int la3d_fit_boxes_p2p(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
                                   int I, int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
                                   uint32_t image_offset, void* workspace, size_t workspace_bytes,
-                                  void* const* peer_records, int n_peers, int rec_f64, la3d_stream_t stream) {
+                                  void* const* peer_records, int n_peers, int rec_f64, void* wait_before_fit,
+                                  la3d_stream_t stream) {
   return la3d::fit_boxes_multi(depth, masks, K, ground, B, I, H, W, mask_is_01, method, yaw_steps, seed, image_offset,
-                               workspace, workspace_bytes, peer_records, n_peers, rec_f64, stream);
+                               workspace, workspace_bytes, peer_records, n_peers, rec_f64, wait_before_fit, stream);
 }
 
 extern "C" int la3d_peer_barrier(uint32_t* const* flags, int rank, int world, uint32_t epoch, int* status,

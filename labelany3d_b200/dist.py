@@ -113,29 +113,49 @@ class ShardedBoxFitter:
         self._flags, self._flag_hdl = f, fh
         self._flag_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in fh.buffer_ptrs])
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._side = torch.cuda.Stream(device=self.device)
+        self._ev_fit = torch.cuda.Event()
+        self._ev_bar = [torch.cuda.Event(), torch.cuda.Event()]
         self._epoch = 0
         self._lib = _lib.load()
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)                       # every rank's fills have landed before the first step
+
+    def wait_gathered(self):
+        """Make the current stream wait until the records of the last call have landed on every rank."""
+        if self.collective == "p2p" and self._epoch:
+            torch.cuda.current_stream(self.device).wait_event(self._ev_bar[self._epoch & 1])
 
     def check_barrier_status(self):
         """Raises if a peer failed to arrive at a barrier (synchronises the device)."""
         if self.collective == "p2p" and int(self._status.item()) != 0:
             raise RuntimeError("la3d_peer_barrier: a peer did not arrive within the timeout")
 
-    def __call__(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, events=None):
-        """Inputs are this rank's block (``[n_local, ...]``).  Returns ``[B_total, I, 64]`` on every rank."""
+    def __call__(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, events=None, wait=True):
+        """Inputs are this rank's block (``[n_local, ...]``).  Returns ``[B_total, I, 64]`` on every rank.
+        ``wait=False`` (p2p only): do not make the current stream wait for the peer barrier; the result is
+        complete once :meth:`wait_gathered` (or a device synchronisation) has passed."""
         if self.collective == "p2p":
             from . import _lib
             self._epoch += 1
-            buf, _ = self._bufs[self._epoch & 1]
+            e = self._epoch
+            buf, _ = self._bufs[e & 1]
+            cur = torch.cuda.current_stream(self.device)
             if self.n_local:
-                peers = self._peer_slots[self._epoch & 1]
-                self.local(depth, K, masks, ground, method, yaw_steps, seed, image_offset=self.start, peers=peers)
+                # the fit may write the peers' buffer e&1 once every rank is past step e-1 (previous barrier)
+                self.local(depth, K, masks, ground, method, yaw_steps, seed, image_offset=self.start,
+                           peers=self._peer_slots[e & 1], wait_before_fit=self._ev_bar[(e - 1) & 1] if e > 1 else None)
+            elif e > 1:
+                cur.wait_event(self._ev_bar[(e - 1) & 1])
+            self._ev_fit.record(cur)
+            self._side.wait_event(self._ev_fit)
             with torch.cuda.device(self.device):
-                rc = self._lib.la3d_peer_barrier(self._flag_ptrs, self.rank, self.world, self._epoch & 0xFFFFFFFF,
-                                                 self._status.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                rc = self._lib.la3d_peer_barrier(self._flag_ptrs, self.rank, self.world, e & 0xFFFFFFFF,
+                                                 self._status.data_ptr(), self._side.cuda_stream)
             _lib.check(rc, "la3d_peer_barrier")
+            self._ev_bar[e & 1].record(self._side)
+            if wait:
+                cur.wait_event(self._ev_bar[e & 1])
             return buf[:self.B_total]
         if self.n_local:
             self.local(depth, K, masks, ground, method, yaw_steps, seed, image_offset=self.start,

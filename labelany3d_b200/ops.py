@@ -242,14 +242,15 @@ class BoxFitter:
         self.records = torch.empty((B, I, REC), dtype=out_dtype, device=self.device)
 
     def __call__(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0, out=None,
-                 events=None, peers=None):
+                 events=None, peers=None, wait_before_fit=None):
         """Fit every (image, instance) box; returns ``records[B,I,64]`` (a buffer owned by the plan
         unless ``out`` is given).  ``events``: optional list of 5 ``torch.cuda.Event``; the four kernels
         are then issued one after the other on the current stream (no overlap) with the events
         recorded before, between and after them: prepare, scan, sample, fit (per-kernel timing
         without a profiler).  ``peers``: list of device pointers (ints) of ``[B,I,64]`` slots in
         peer-mapped record buffers; the fit kernel then writes every record to all of them
-        (``la3d_fit_boxes_p2p``) instead of to ``out``."""
+        (``la3d_fit_boxes_p2p``) instead of to ``out``; ``wait_before_fit``: a ``torch.cuda.Event`` the
+        stream waits for between the sampler and the fit kernel (the previous step's peer barrier)."""
         B, I, H, W = self.shape
         # the fit gathers only 500 depth values per box, so the depth maps may stay in pinned host memory
         depth = _need_cuda("depth", depth, torch.float32, pinned_ok=True)
@@ -277,7 +278,8 @@ class BoxFitter:
                 rc = lib.la3d_fit_boxes_p2p(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01,
                                             _method_id(method), int(yaw_steps), int(seed) & 0xFFFFFFFF,
                                             int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace), self.ws_bytes,
-                                            arr, len(peers), f64, st)
+                                            arr, len(peers), f64,
+                                            None if wait_before_fit is None else wait_before_fit.cuda_event, st)
                 _lib.check(rc, "la3d_fit_boxes_p2p")
             elif events is None:
                 rc = lib.la3d_fit_boxes(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01,

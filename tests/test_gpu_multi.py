@@ -26,12 +26,13 @@ def _worker(rank, world, port, out_dir):
     res = {}
     for coll in ("p2p", "nccl"):
         fit = la_dist.ShardedBoxFitter(B_total, I, H, W, device=dev, collective=coll)
-        for step in range(3):                              # several steps: epochs, double buffering
-            rec = fit(depth[sl], K[sl], masks[sl], ground[sl], "sweep", 36, seed=11 + step)
+        for step in range(5):                              # several steps: epochs, double buffering, deferred barriers
+            rec = fit(depth[sl], K[sl], masks[sl], ground[sl], "sweep", 36, seed=11 + step, wait=(step % 2 == 0))
+        fit.wait_gathered()
         torch.cuda.synchronize()
         fit.check_barrier_status()
         res[coll] = rec.cpu().numpy().copy()
-    single = ops.fit_boxes(depth, K, masks, ground, "sweep", 36, seed=13).cpu().numpy()
+    single = ops.fit_boxes(depth, K, masks, ground, "sweep", 36, seed=15).cpu().numpy()
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.stack([res["p2p"], res["nccl"], single]))
     dist.barrier()
     dist.destroy_process_group()

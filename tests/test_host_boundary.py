@@ -62,7 +62,7 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
         "la3d_sample_ranks": lambda: lib.la3d_sample_ranks(None, None, 1, 1, 4, 4, None, None, None),
         "la3d_fit_scanned": lambda: lib.la3d_fit_scanned(None, None, None, None, None, 1, 1, 4, 4, 0, 0, None, 0, None),
         "la3d_fit_boxes": lambda: lib.la3d_fit_boxes(None, None, None, None, 1, 1, 4, 4, 1, 0, 0, 0, 0, None, 0, None, 0, None),
-        "la3d_fit_boxes_p2p": lambda: lib.la3d_fit_boxes_p2p(None, None, None, None, 1, 1, 4, 4, 1, 0, 0, 0, 0, None, 0, None, 1, 0, None),
+        "la3d_fit_boxes_p2p": lambda: lib.la3d_fit_boxes_p2p(None, None, None, None, 1, 1, 4, 4, 1, 0, 0, 0, 0, None, 0, None, 1, 0, None, None),
         "la3d_peer_barrier": lambda: lib.la3d_peer_barrier(None, 0, 1, 1, None, None),
         "la3d_fit_points": lambda: lib.la3d_fit_points(None, None, None, None, None, 1, 0, 0, None, 0, None),
         "la3d_project_points": lambda: lib.la3d_project_points(None, None, None, 1, None, None),
