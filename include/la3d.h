@@ -186,6 +186,44 @@ int la3d_fit_boxes(const float* depth, const uint8_t* masks, const double* K, co
                    void* workspace, size_t workspace_bytes, void* records, int rec_f64, la3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Mask stacks from COCO run-length annotations (input side of the path).  Replaces the host-side
+ * `mask_utils.decode(rle)` per annotation of read_bounding_boxes_segmentations, src/util.py:361-370
+ * (COCO RLE: column-major runs alternating 0, 1, 0, ... - the format the reference's own encoder
+ * binary_mask_to_rle, src/download_coconut.py:167-175, writes): one CTA per plane turns the runs
+ * straight into the bit plane and quarter counts la3d_mask_scan would have produced from the decoded
+ * byte mask, which therefore never exists (neither in HBM nor on the bus).
+ *   run_counts   run lengths of all planes back to back, uint32
+ *   run_offsets  [planes+1] int64: plane p owns run_counts[run_offsets[p] .. run_offsets[p+1])
+ *   max_runs     upper bound on the runs of one plane the CALLER knows (sizes the shared-memory copy of
+ *                the run ends); 0 = unknown
+ *   ends_ws      nullable [total runs] uint32 scratch, used by planes with more than max_runs runs
+ *                (or by all when max_runs is 0 or above 32768)
+ *   bits / chunk_counts: as la3d_mask_scan
+ *   status       [planes] int32 (out): 0 ok; 1 the runs cover more than H*W pixels (pycocotools 2.0
+ *                would write out of bounds; here the in-image part is decoded); 2 more runs than
+ *                max_runs and no ends_ws (plane left empty)
+ * ------------------------------------------------------------------------- */
+int la3d_rle_decode(const uint32_t* run_counts, const int64_t* run_offsets, int planes, int H, int W, int max_runs,
+                    uint32_t* ends_ws, uint32_t* bits, uint32_t* chunk_counts, int32_t* status, la3d_stream_t stream);
+
+/* The box fit from bit planes that already exist (la3d_rle_decode, or an earlier la3d_mask_scan):
+ * la3d_fit_prepare -> la3d_sample_ranks -> la3d_fit_scanned on `stream`, workspace of
+ * la3d_fit_bits_workspace_bytes(B, I) bytes, 256-byte aligned. */
+size_t la3d_fit_bits_workspace_bytes(int B, int I);
+int la3d_fit_boxes_bits(const float* depth, const uint32_t* bits, const uint32_t* chunk_counts, const double* K,
+                        const double* ground, int B, int I, int H, int W, int method, int yaw_steps, uint32_t seed,
+                        uint32_t image_offset, void* workspace, size_t workspace_bytes, void* records, int rec_f64,
+                        la3d_stream_t stream);
+
+/* la3d_fit_boxes with run-length masks as the input: three launches (decode with the preparation riding
+ * in its grid, subsample ranks, fit).  `workspace` as for la3d_fit_boxes (la3d_fit_workspace_bytes);
+ * rle_status [B*I] as la3d_rle_decode's `status`. */
+int la3d_fit_boxes_rle(const float* depth, const uint32_t* run_counts, const int64_t* run_offsets, int max_runs,
+                       uint32_t* ends_ws, const double* K, const double* ground, int B, int I, int H, int W, int method,
+                       int yaw_steps, uint32_t seed, uint32_t image_offset, void* workspace, size_t workspace_bytes,
+                       int32_t* rle_status, void* records, int rec_f64, la3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Multi-GPU form (images sharded across the GPUs of one NVLink / NVSwitch node, the reference's
  * --start_index/--end_index/--gpu_idx split of src/batch_scripts/whole.py:25-27,42): the fit kernel
  * writes every record straight into the gathered record buffer of EVERY rank through peer memory

@@ -37,6 +37,10 @@ SIGNATURES = {
     "la3d_iou_matrix": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "la3d_box2d_from_corners": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "la3d_masked_ratio_median": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "la3d_rle_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "la3d_fit_bits_workspace_bytes": (_sz, [_i, _i]),
+    "la3d_fit_boxes_bits": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _i, _vp]),
+    "la3d_fit_boxes_rle": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _vp, _i, _vp]),
     "la3d_project_points": (_i, [_vp, _vp, _vp, C.c_longlong, _vp, _vp]),
 }
 

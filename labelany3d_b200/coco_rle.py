@@ -1,0 +1,66 @@
+"""Host side of the COCO run-length format: the compressed ``counts`` string of COCO / COCONUT
+annotations -> run lengths, and run lists -> the flat arrays ``la3d_rle_decode`` takes.
+
+The reference hands the string to pycocotools (``mask_utils.decode``, ``src/util.py:364-367``), whose
+``rleFrString`` parses it on the host as well; the parsing below is that format in vectorised NumPy
+(5 payload bits per character starting at ASCII 48, bit ``0x20`` = "more characters follow", bit
+``0x10`` of the last character = sign, and from the fourth run on the stored value is the difference
+to the run two places back).  Turning runs into masks is the GPU's job (``csrc/rle.cu``).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def counts_from_string(s):
+    """Run lengths (``uint32`` array) of a compressed ``counts`` string (``str`` or ``bytes``)."""
+    if isinstance(s, str):
+        s = s.encode("utf-8")
+    c = np.frombuffer(s, dtype=np.uint8).astype(np.int64) - 48
+    if c.size == 0:
+        return np.zeros(0, dtype=np.uint32)
+    more = (c & 0x20) != 0
+    if more[-1]:
+        raise ValueError("truncated RLE string: the last character announces another one")
+    last = ~more                                           # last character of every run
+    run_id = np.concatenate(([0], np.cumsum(last)[:-1]))   # which run a character belongs to
+    starts = np.flatnonzero(np.concatenate(([True], last[:-1])))
+    k = np.arange(c.size) - starts[run_id]                 # position of the character inside its run
+    if k.max() > 12:
+        raise ValueError("RLE string holds a run of more than 13 characters (beyond 64 bits)")
+    n = int(run_id[-1]) + 1
+    x = np.zeros(n, dtype=np.int64)
+    np.add.at(x, run_id, (c & 0x1F) << (5 * k))
+    neg = last & ((c & 0x10) != 0)                          # sign bit of the last character: extend it
+    x[run_id[neg]] |= np.int64(-1) << (5 * (k[neg] + 1))
+    # runs 3, 5, 7, ... add to run 1's chain, runs 4, 6, ... to run 2's; run 0 stands alone
+    out = x.copy()
+    out[1::2] = np.cumsum(x[1::2])
+    if n > 2:
+        out[2::2] = np.cumsum(x[2::2])
+    return (out & 0xFFFFFFFF).astype(np.uint32)
+
+
+def runs_of(segmentation):
+    """``(run lengths uint32, (h, w))`` of one annotation's RLE dict (``counts``: str, bytes or list)."""
+    h, w = (int(v) for v in segmentation["size"])
+    counts = segmentation["counts"]
+    if isinstance(counts, (str, bytes)):
+        runs = counts_from_string(counts)
+    else:
+        runs = np.asarray(counts, dtype=np.int64)
+        if runs.size and (runs.min() < 0 or runs.max() > 0xFFFFFFFF):
+            raise ValueError("run lengths must fit an unsigned 32-bit integer")
+        runs = runs.astype(np.uint32)
+    return runs, (h, w)
+
+
+def pack_runs(run_lists):
+    """``(counts uint32[total], offsets int64[P+1], max_runs)`` for a list of run-length arrays."""
+    sizes = np.array([len(r) for r in run_lists], dtype=np.int64)
+    offsets = np.zeros(len(run_lists) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    counts = (np.concatenate([np.asarray(r, dtype=np.uint32) for r in run_lists]) if len(run_lists) and offsets[-1]
+              else np.zeros(0, dtype=np.uint32))
+    return counts, offsets, int(sizes.max()) if len(run_lists) else 0

@@ -134,6 +134,81 @@ extern "C" int la3d_fit_boxes(const float* depth, const uint8_t* masks, const do
                                workspace, workspace_bytes, &records, 1, rec_f64, nullptr, stream);
 }
 
+// ---- the path from bit planes (no byte masks): annotations decoded on the device, or planes kept from an earlier scan
+namespace la3d {
+struct BitsWorkspace {
+  int32_t* counts;
+  int32_t* ranks;
+  void* prep;
+  size_t prep_bytes;
+  size_t bytes;
+};
+static BitsWorkspace carve_bits(void* base, int B, int I) {
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t planes = (size_t)B * I;
+  unsigned char* p = static_cast<unsigned char*>(base);
+  BitsWorkspace w{};
+  size_t off = 0;
+  w.counts = reinterpret_cast<int32_t*>(p + off);  off = up(off + planes * 4);
+  w.ranks = reinterpret_cast<int32_t*>(p + off);   off = up(off + planes * LA3D_SUBSAMPLE * 4);
+  w.prep = p + off;  w.prep_bytes = la3d_prep_bytes(B, I);  off = up(off + w.prep_bytes);
+  w.bytes = off;
+  return w;
+}
+}  // namespace la3d
+
+extern "C" size_t la3d_fit_bits_workspace_bytes(int B, int I) {
+  if (B <= 0 || I <= 0) return 0;
+  return la3d::carve_bits(nullptr, B, I).bytes;
+}
+
+extern "C" int la3d_fit_boxes_bits(const float* depth, const uint32_t* bits, const uint32_t* chunk_counts, const double* K,
+                                   const double* ground, int B, int I, int H, int W, int method, int yaw_steps,
+                                   uint32_t seed, uint32_t image_offset, void* workspace, size_t workspace_bytes,
+                                   void* records, int rec_f64, la3d_stream_t stream) {
+  using namespace la3d;
+  LA3D_REQUIRE(depth && bits && chunk_counts && K && workspace && records, "null pointer");
+  LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
+  LA3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+  const BitsWorkspace w = carve_bits(workspace, B, I);
+  if (workspace_bytes < w.bytes) {
+    set_error("la3d_fit_boxes_bits: workspace of %zu bytes, %zu needed", workspace_bytes, w.bytes);
+    return LA3D_ENOMEM;
+  }
+  int rc = la3d_fit_prepare(K, ground, B, I, seed, image_offset, w.prep, w.prep_bytes, stream);
+  if (rc) return rc;
+  rc = la3d_sample_ranks(chunk_counts, w.prep, B, I, H, W, w.counts, w.ranks, stream);
+  if (rc) return rc;
+  return la3d_fit_scanned(depth, w.prep, bits, chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, records, rec_f64, stream);
+}
+
+extern "C" int la3d_fit_boxes_rle(const float* depth, const uint32_t* run_counts, const int64_t* run_offsets, int max_runs,
+                                  uint32_t* ends_ws, const double* K, const double* ground, int B, int I, int H, int W,
+                                  int method, int yaw_steps, uint32_t seed, uint32_t image_offset, void* workspace,
+                                  size_t workspace_bytes, int32_t* rle_status, void* records, int rec_f64,
+                                  la3d_stream_t stream) {
+  using namespace la3d;
+  LA3D_REQUIRE(depth && run_counts && run_offsets && K && workspace && rle_status && records, "null pointer");
+  LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
+  LA3D_REQUIRE(I <= 8192, "at most 8192 instances per image");
+  LA3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+  const Workspace w = carve(workspace, B, I, H, W);
+  if (workspace_bytes < w.bytes) {
+    set_error("la3d_fit_boxes_rle: workspace of %zu bytes, %zu needed", workspace_bytes, w.bytes);
+    return LA3D_ENOMEM;
+  }
+  // one launch: a CTA per plane decodes its runs into bits + quarter counts, plus the CTAs that prepare the batch
+  const PrepView pv = prep_view(w.prep, B, I, prep_blocks(I));
+  const PrepArgs pa{K, ground, B, I, seed + image_offset, pv};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = launch_rle_decode(run_counts, run_offsets, B * I, H, W, max_runs, ends_ws, w.bits, w.chunk_counts, rle_status, &pa, s);
+  if (rc) return rc;
+  rc = launch_sample(w.chunk_counts, pv, B, I, (int)la3d_chunks_per_plane(H, W), w.counts, w.ranks, s, false);
+  if (rc) return rc;
+  void* rec = records;
+  return fit_scanned_multi(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, &rec, 1, rec_f64, s, false);
+}
+
 extern "C" int la3d_fit_boxes_p2p(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
                                   int I, int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
                                   uint32_t image_offset, void* workspace, size_t workspace_bytes,

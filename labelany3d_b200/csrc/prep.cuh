@@ -142,6 +142,10 @@ __device__ __forceinline__ void prep_body(const PrepArgs& pa, int first) {
 int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
                      uint32_t* chunk_counts, const PrepArgs* prep, cudaStream_t s);
 
+int launch_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes, int H, int W, int max_runs,
+                      uint32_t* ends_ws, uint32_t* bits, uint32_t* chunk_counts, int32_t* status, const PrepArgs* prep,
+                      cudaStream_t s);
+
 int fit_scanned_multi(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
                       const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
                       void* const* records, int n_out, int rec_f64, cudaStream_t stream, bool pdl = false);

@@ -1,0 +1,254 @@
+// COCO run-length masks -> bit planes + quarter counts on sm_100a.
+//
+// The reference builds its bool [I,H,W] mask stack on the host by decoding COCO / COCONUT
+// run-length annotations one by one (mask_utils.decode, src/util.py:361-370) and only then
+// hands it to the path.  Here the runs are the input: one CTA per plane turns them straight
+// into what la3d_mask_scan would have produced from the decoded bytes (bit k of word j =
+// row-major pixel 32 j + k; one count byte per 128-pixel quarter of a 512-pixel chunk), so the
+// byte masks (I bytes per pixel, the dominant HBM stream of the scanned path and 8x the bits
+// over PCIe) never exist.  Integer work: bit-exact.
+//
+// COCO runs are COLUMN-major (pixel (y,x) has run position x*H + y), the bit planes are
+// row-major, so the kernel is a bit transposition:
+//   1. inclusive prefix sums of the plane's run lengths -> run ends E[] (shared memory);
+//   2. per band of 32 rows and strip of 32 columns: lane l owns column 32 s + l, finds the run
+//      holding its first pixel by binary search over E[], walks the (few) runs crossing its
+//      32 pixels into a 32-bit column word, and the warp transposes the 32x32 bit tile with
+//      five shuffle rounds (skipped when the tile is empty); rows go to a padded staging tile;
+//   3. a band of 32 rows is exactly W words of the plane's bit stream (32*W pixels), so the CTA
+//      re-packs the staged rows (funnel shifts when W is not a multiple of 32) into finished
+//      words, stores them coalesced, and adds their popcounts to the quarter counts
+//      (a segmented warp reduction, then one red.global per quarter and warp).
+//
+// kPrep: like the mask scan, the first ceil(B/8) CTAs of the launch may instead run the
+// mask-independent preparation of the batch (prep.cuh), so la3d_fit_boxes_rle stays at three launches.
+#include "prep.cuh"
+
+namespace la3d {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxSmemRuns = 32768;            // 128 KB of run ends at most in shared memory
+
+struct RleArgs {
+  const uint32_t* counts;      // run lengths of all planes, back to back
+  const long long* offsets;    // [planes+1] first run of every plane
+  uint32_t* ends_ws;           // nullable [total runs]: run ends of planes that do not fit shared memory
+  int H, W, HW, chunks, smem_runs;
+  uint32_t* bits;
+  uint32_t* chunk_counts;
+  int32_t* status;
+};
+
+// a[l] bit j  ->  a[j] bit l  across the warp (recursive block swap, five rounds).
+__device__ __forceinline__ uint32_t transpose32(uint32_t a, int lane) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    // bits j with (j & s) == 0
+    const uint32_t low = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t other = __shfl_xor_sync(kFull, a, s);
+    a = (lane & s) ? ((a & ~low) | ((other >> s) & low)) : ((a & low) | ((other << s) & ~low));
+  }
+  return a;
+}
+
+// number of run ends <= q, i.e. the index of the run that holds position q
+__device__ __forceinline__ int run_of(const uint32_t* __restrict__ E, int m, uint32_t q) {
+  int lo = 0, hi = m;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (E[mid] <= q) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ uint32_t bit_range(uint32_t a, uint32_t b) {       // bits [a, b), 0 <= a < b <= 32
+  const uint32_t hi = b >= 32u ? 0xffffffffu : ((1u << b) - 1u);
+  return hi & ~((1u << a) - 1u);
+}
+
+template <bool kPrep>
+__global__ void __launch_bounds__(kThreads) rle_decode_kernel(RleArgs a, PrepArgs pa) {
+  extern __shared__ __align__(16) uint32_t dyn[];
+  __shared__ unsigned long long warp_tot[kWarps];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int plane = blockIdx.x;
+  if (kPrep) {
+    const int prep_ctas = (pa.B + kWarps - 1) / kWarps;           // one warp per image
+    if (plane < prep_ctas) { prep_body<kThreads>(pa, plane * kWarps); return; }   // CTA-uniform
+    plane -= prep_ctas;
+  }
+  const int H = a.H, W = a.W, HW = a.HW;
+  const int pitch = (W + 31) >> 5;               // 32-column strips per row
+  const int P = pitch | 1;                       // staging pitch: odd, so a tile's 32 rows hit 32 banks
+  uint32_t* stage = dyn;                         // [32][P]
+  uint32_t* ends_smem = dyn + 32 * P;            // [smem_runs]
+
+  const long long r0 = a.offsets[plane];
+  const long long m_ll = a.offsets[plane + 1] - r0;
+  int m = (int)min(m_ll, (long long)0x7fffffff);
+  const uint32_t* cnt = a.counts + r0;
+  uint32_t* E = ends_smem;
+  int st = 0;
+  if (m > a.smem_runs) {
+    if (a.ends_ws) E = a.ends_ws + r0;
+    else { st = 2; m = 0; }                      // more runs than the caller announced and no workspace: refuse
+  }
+
+  // ---- 1. run ends: inclusive prefix sums, clamped to HW+1 (anything beyond the image is equal) ----
+  const int per = (m + kThreads - 1) / kThreads;
+  const int j_lo = min(tid * per, m), j_hi = min(j_lo + per, m);
+  unsigned long long run = 0;
+  for (int j = j_lo; j < j_hi; ++j) run += cnt[j];
+  unsigned long long incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long up = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  unsigned long long base = incl - run, total = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    if (w < warp) base += warp_tot[w];
+    total += warp_tot[w];
+  }
+  for (int j = j_lo; j < j_hi; ++j) {
+    base += cnt[j];
+    E[j] = (uint32_t)min(base, (unsigned long long)HW + 1ull);
+  }
+  if (total > (unsigned long long)HW) st = 1;
+  if (tid == 0) a.status[plane] = st;
+  uint32_t* cc = a.chunk_counts + (size_t)plane * a.chunks;
+  for (int c = tid; c < a.chunks; c += kThreads) cc[c] = 0u;
+  __syncthreads();
+
+  // columns that can hold a set pixel: from the first 1-run's start to the last 1-run's end
+  int x_lo = W, x_hi = -1;
+  if (m >= 2) {
+    const uint32_t first = E[0];
+    const uint32_t last = min((m & 1) ? E[m - 2] : E[m - 1], (uint32_t)HW);
+    if (last > first) { x_lo = (int)(first / (uint32_t)H); x_hi = (int)((last - 1u) / (uint32_t)H); }
+  }
+
+  // ---- 2./3. bands of 32 rows = W words of the bit stream each ----
+  const long long words_total = (long long)a.chunks * kChunkWords;
+  uint32_t* out_bits = a.bits + (size_t)plane * words_total;
+  const bool aligned = (W & 31) == 0;
+  for (long long w_base = 0; w_base < words_total; w_base += W) {
+    const long long y0_ll = (w_base / W) * 32;
+    const int nrows = y0_ll >= H ? 0 : min(32, H - (int)y0_ll);
+    const int y0 = (int)min(y0_ll, (long long)H);
+    for (int s = warp; s < pitch; s += kWarps) {
+      const int x = 32 * s + lane;
+      uint32_t word = 0;
+      if (nrows > 0 && x < W && x >= x_lo && x <= x_hi) {
+        const uint32_t q0 = (uint32_t)x * (uint32_t)H + (uint32_t)y0, q1 = q0 + (uint32_t)nrows;
+        int k = run_of(E, m, q0);
+        uint32_t pos = q0;
+        while (pos < q1 && k < m) {
+          const uint32_t e = E[k];
+          const uint32_t end = min(e, q1);
+          if ((k & 1) && end > pos) word |= bit_range(pos - q0, end - q0);
+          pos = end;
+          if (e <= q1) ++k;
+        }
+      }
+      if (__any_sync(kFull, word != 0u)) word = transpose32(word, lane);      // now lane = row, bit = column
+      stage[lane * P + s] = word;
+    }
+    __syncthreads();
+    const int n_words = (int)min((long long)W, words_total - w_base);
+    for (int base_w = warp * 32; base_w < n_words; base_w += kThreads) {      // warp-uniform trip count
+      const int wi = base_w + lane;
+      const bool active = wi < n_words;
+      uint32_t out = 0;
+      if (active) {
+        if (aligned) {
+          const int r = wi / pitch;
+          out = stage[r * P + (wi - r * pitch)];
+        } else {
+          const uint32_t p = 32u * (uint32_t)wi;
+          int r = (int)(p / (uint32_t)W);
+          int x = (int)(p - (uint32_t)r * (uint32_t)W);
+          int got = 0;
+          while (got < 32 && r < 32) {
+            const int n = min(32 - got, W - x);
+            const int c = x >> 5;
+            const uint32_t w0 = stage[r * P + c];
+            const uint32_t w1 = (c + 1 < pitch) ? stage[r * P + c + 1] : 0u;
+            uint32_t v = __funnelshift_r(w0, w1, x & 31);
+            if (n < 32) v &= (1u << n) - 1u;
+            out |= v << got;
+            got += n; ++r; x = 0;
+          }
+        }
+        out_bits[w_base + wi] = out;
+      }
+      // quarter counts: lanes of one 4-word quarter are neighbours; sum them, one red per quarter
+      const long long wg = w_base + wi;
+      const uint32_t key = active ? (uint32_t)(wg >> 2) : (0x80000000u | (uint32_t)lane);
+      uint32_t v = __popc(out);
+      const uint32_t k1 = __shfl_down_sync(kFull, key, 1), v1 = __shfl_down_sync(kFull, v, 1);
+      if (lane + 1 < 32 && k1 == key) v += v1;
+      const uint32_t k2 = __shfl_down_sync(kFull, key, 2), v2 = __shfl_down_sync(kFull, v, 2);
+      if (lane + 2 < 32 && k2 == key) v += v2;
+      const uint32_t kp = __shfl_up_sync(kFull, key, 1);
+      const bool head = lane == 0 || kp != key;
+      if (active && head && v) atomicAdd(&cc[wg >> 4], v << (8 * (int)((wg >> 2) & 3)));
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+// prep == nullptr: the plain decode.  Otherwise ceil(prep->B / 8) extra CTAs at the front of the grid prepare the batch.
+int launch_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes, int H, int W, int max_runs,
+                      uint32_t* ends_ws, uint32_t* bits, uint32_t* chunk_counts, int32_t* status, const PrepArgs* prep,
+                      cudaStream_t s) {
+  LA3D_REQUIRE(counts && offsets && bits && chunk_counts && status, "null pointer");
+  LA3D_REQUIRE(planes > 0 && H > 0 && W > 0, "non-positive shape");
+  LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
+  LA3D_REQUIRE(W <= 32768, "image wider than 32768 pixels");
+  LA3D_REQUIRE(max_runs >= 0, "negative max_runs");
+  static_assert(sizeof(long long) == sizeof(int64_t), "offsets are 64-bit");
+  RleArgs a{};
+  a.counts = counts; a.offsets = reinterpret_cast<const long long*>(offsets); a.ends_ws = ends_ws;
+  a.H = H; a.W = W; a.HW = H * W; a.chunks = (int)la3d_chunks_per_plane(H, W);
+  a.smem_runs = max_runs > kMaxSmemRuns ? 0 : max_runs;      // too many for shared memory: every plane uses ends_ws
+  if (a.smem_runs == 0 && !ends_ws && max_runs > 0) {
+    set_error("la3d_rle_decode: %d runs per plane need the ends_ws workspace (more than %d)", max_runs, kMaxSmemRuns);
+    return LA3D_EINVAL;
+  }
+  a.bits = bits; a.chunk_counts = chunk_counts; a.status = status;
+  const int P = ((W + 31) >> 5) | 1;
+  const size_t smem = ((size_t)32 * P + (size_t)a.smem_runs) * 4;
+  LA3D_REQUIRE(smem <= 200 * 1024, "image too wide for the staging tile plus the run ends in shared memory");
+  const long long ctas = (long long)planes + (prep ? (prep->B + kWarps - 1) / kWarps : 0);
+  LA3D_REQUIRE(ctas < (1ll << 31), "grid too large");
+  const PrepArgs pa = prep ? *prep : PrepArgs{};
+  // opt in to more dynamic shared memory only when a launch needs more than any before it
+  static size_t opted[2] = {16 * 1024, 16 * 1024};
+  if (smem > opted[prep ? 1 : 0]) {
+    if (prep) LA3D_CUDA(cudaFuncSetAttribute(rle_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else LA3D_CUDA(cudaFuncSetAttribute(rle_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    opted[prep ? 1 : 0] = smem;
+  }
+  if (prep) rle_decode_kernel<true><<<(unsigned)ctas, kThreads, smem, s>>>(a, pa);
+  else rle_decode_kernel<false><<<(unsigned)ctas, kThreads, smem, s>>>(a, pa);
+  LA3D_CUDA(cudaGetLastError());
+  return LA3D_OK;
+}
+
+}  // namespace la3d
+
+extern "C" int la3d_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes, int H, int W, int max_runs,
+                               uint32_t* ends_ws, uint32_t* bits, uint32_t* chunk_counts, int32_t* status,
+                               la3d_stream_t stream) {
+  return la3d::launch_rle_decode(counts, offsets, planes, H, W, max_runs, ends_ws, bits, chunk_counts, status, nullptr,
+                                 static_cast<cudaStream_t>(stream));
+}

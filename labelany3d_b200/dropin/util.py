@@ -1,7 +1,9 @@
 """Drop-in for the hot-path functions of the reference's ``src/util.py``:
 ``depth_to_points`` (``:52-75``), ``project_to_2d`` (``:227-229``), ``draw_cube`` (``:232-289``)
 and, either side of the box fit, ``analyze_mask`` (``:291-326``), ``get_maximum_height``
-(``:328-335``) and ``align_to_depth_match`` (``:464-494``).  Same names, signatures and return
+(``:328-335``), ``read_bounding_boxes_segmentations`` (``:337-382``, with
+``create_boolean_mask_from_polygon`` ``:386-415`` and ``replace_categories_with_supercategories``
+``:452-461``) and ``align_to_depth_match`` (``:464-494``).  Same names, signatures and return
 types; the arithmetic runs on the B200.
 
 Only these are provided: the rest of the reference's ``util.py`` is model / IO glue outside this
@@ -113,6 +115,143 @@ def get_maximum_height(binary_mask):
     if s[_ops.STAT_ROWS] == 0:
         return 0
     return np.int64(int(s[_ops.STAT_LAST_ROW]) - int(s[_ops.STAT_FIRST_ROW]) + 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# annotations -> mask stack (the loader in front of the path)
+# ---------------------------------------------------------------------------------------------
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "coco_category_names.json")) as _f:
+    COCO_CATEGORIES = {int(k): v for k, v in json.load(_f).items()}       # id -> name, src/util.py:419-449
+
+
+def replace_categories_with_supercategories(category_ids, json_file_path=None):
+    """Category names of COCO / COCONUT ids, ``"unknown"`` for anything else (``src/util.py:452-461``)."""
+    return [COCO_CATEGORIES.get(c, "unknown") for c in category_ids]
+
+
+def create_boolean_mask_from_polygon(image_shape, segmentation):
+    """``(bool mask [image_shape[1], image_shape[0]], get_maximum_height(mask))`` of a polygon list or an
+    RLE dict (``src/util.py:386-415``).  Polygons are filled on the host by OpenCV like the reference
+    (its scan conversion is the format's definition); RLE runs are decoded on the GPU."""
+    import cv2
+    mask = np.zeros((image_shape[1], image_shape[0]), dtype=np.uint8)
+    if isinstance(segmentation, list):
+        for polygon in segmentation:
+            points = np.array(polygon).reshape(-1, 2).astype(np.int32)
+            cv2.fillPoly(mask, [points], color=1)
+    elif isinstance(segmentation, dict):
+        from labelany3d_b200 import coco_rle
+        runs, (h, w) = coco_rle.runs_of(segmentation)
+        counts, offsets, max_runs = coco_rle.pack_runs([runs])
+        dev = _device()
+        bits, _, status = _ops.rle_decode(torch.as_tensor(counts.view(np.int32), device=dev),
+                                          torch.as_tensor(offsets, device=dev), h, w, max_runs)
+        if int(status[0]) != 0:
+            raise ValueError("Invalid RLE mask representation")
+        mask = np.maximum(mask, _ops.unpack_bits(bits, h, w)[0].astype(np.uint8))
+    boolean_mask = mask.astype(bool)
+    return boolean_mask, get_maximum_height(boolean_mask)
+
+
+def read_bounding_boxes_segmentations(annotations_path_or_list, image_size):
+    """``(bboxes, masks bool [I,H,W], arange(I), category names)`` of one image's COCO / COCONUT
+    annotations (``src/util.py:337-382``): crowd annotations are skipped; an instance is kept when its
+    mask spans more than 6.25 % of the image height, puts fewer than 10 pixels into the 10-pixel border
+    bands and covers at least 100 pixels.
+
+    All run-length annotations of the image are decoded in ONE launch straight into bit planes
+    (``la3d_rle_decode``), polygon masks (filled by OpenCV on the host like the reference) are scanned
+    into the same layout, and one ``la3d_mask_stats`` launch yields every integer the admission test
+    needs; only the kept planes come back to the host.  ``image_size = (width, height)``."""
+    from labelany3d_b200 import coco_rle
+    if isinstance(annotations_path_or_list, (str, os.PathLike)):
+        with open(annotations_path_or_list, "r") as file:
+            annotations = json.load(file)
+    else:
+        annotations = annotations_path_or_list
+
+    # what each annotation is: ("crowd",) | ("none",) | ("rle", runs, (h, w)) | ("poly", mask, height)
+    kinds = []
+    for annotation in annotations:
+        if annotation["iscrowd"]:
+            kinds.append(("crowd",))
+        elif "segmentation" not in annotation:
+            kinds.append(("none",))
+        else:
+            seg = annotation["segmentation"]
+            if isinstance(seg, dict) and "counts" in seg:
+                runs, size = coco_rle.runs_of(seg)
+                kinds.append(("rle", runs, size))
+            elif isinstance(seg, list):
+                mask = np.zeros((image_size[1], image_size[0]), dtype=np.uint8)
+                import cv2
+                for polygon in seg:
+                    cv2.fillPoly(mask, [np.array(polygon).reshape(-1, 2).astype(np.int32)], color=1)
+                kinds.append(("poly", mask.astype(bool)))
+            else:
+                raise KeyError("counts")            # a dict without run lengths: the reference fails on rle['counts']
+
+    dev = _device() if any(k[0] in ("rle", "poly") for k in kinds) else None
+    stats = {}                                     # annotation index -> the 8 integers of la3d_mask_stats
+    planes = {}                                    # annotation index -> (bits tensor, row, (h, w)) for RLE planes
+    by_size = {}
+    for idx, k in enumerate(kinds):
+        if k[0] == "rle":
+            by_size.setdefault(k[2], []).append(idx)
+    for (h, w), members in by_size.items():
+        counts, offsets, max_runs = coco_rle.pack_runs([kinds[i][1] for i in members])
+        bits, _, status = _ops.rle_decode(torch.as_tensor(counts.view(np.int32), device=dev),
+                                          torch.as_tensor(offsets, device=dev), h, w, max_runs)
+        if bool((status != 0).any()):
+            raise ValueError("Invalid RLE mask representation")
+        st = _ops.mask_stats(bits, h, w, 10).cpu().numpy().astype(np.int64)
+        for row, i in enumerate(members):
+            stats[i] = st[row]
+            planes[i] = (bits, row, (h, w))
+    poly = [i for i, k in enumerate(kinds) if k[0] == "poly"]
+    if poly:
+        stack = torch.as_tensor(np.ascontiguousarray(np.stack([kinds[i][1] for i in poly])), device=dev)
+        pbits, _ = _ops.mask_scan(stack)
+        st = _ops.mask_stats(pbits, image_size[1], image_size[0], 10).cpu().numpy().astype(np.int64)
+        for row, i in enumerate(poly):
+            stats[i] = st[row]
+
+    bboxes, kept, category_ids = [], [], []
+    for idx, (annotation, k) in enumerate(zip(annotations, kinds)):
+        if k[0] == "crowd":
+            print("Skip crowd annotation")
+            continue
+        if k[0] == "none":
+            continue
+        s = stats[idx]
+        if k[0] == "rle":
+            height = s[_ops.STAT_ROWS]                                   # np.sum(np.any(mask, axis=1)), :369-370
+        else:
+            height = 0 if s[_ops.STAT_ROWS] == 0 else s[_ops.STAT_LAST_ROW] - s[_ops.STAT_FIRST_ROW] + 1   # :328-335
+        is_truncated = s[_ops.STAT_TOP] + s[_ops.STAT_BOTTOM] + s[_ops.STAT_LEFT] + s[_ops.STAT_RIGHT] >= 10
+        is_scaleable = s[_ops.STAT_AREA] >= 100
+        if height / image_size[1] > 0.0625 and not is_truncated and is_scaleable:
+            kept.append(idx)
+            category_ids.append(annotation["category_id"])
+            bboxes.append(annotation["bbox"])
+        else:
+            print("Too small segmentation")
+
+    segmentation_mask = []
+    fetched = {}                                   # one device->host copy per decode launch, kept rows only
+    for idx in kept:
+        if kinds[idx][0] == "poly":
+            segmentation_mask.append(kinds[idx][1])
+        else:
+            bits, row, (h, w) = planes[idx]
+            key = id(bits)
+            if key not in fetched:
+                rows = [planes[j][1] for j in kept if kinds[j][0] == "rle" and planes[j][0] is bits]
+                sel = torch.as_tensor(rows, device=bits.device)
+                fetched[key] = dict(zip(rows, _ops.unpack_bits(bits.index_select(0, sel), h, w)))
+            segmentation_mask.append(fetched[key][row])
+    return (bboxes, np.array(segmentation_mask), np.arange(len(segmentation_mask)),
+            replace_categories_with_supercategories(category_ids))
 
 
 # ---------------------------------------------------------------------------------------------

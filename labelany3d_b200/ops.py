@@ -121,6 +121,43 @@ def mask_scan(masks, thin=None):
     return bits, cc
 
 
+def rle_decode(run_counts, run_offsets, H, W, max_runs=0):
+    """COCO run-length planes -> ``(bits, chunk_counts, status)`` in the layout of :func:`mask_scan`,
+    without the byte masks (``la3d_rle_decode``; replaces ``mask_utils.decode`` of
+    ``src/util.py:361-370``).  ``run_counts`` uint32-valued int32/uint32 CUDA tensor of all planes'
+    column-major run lengths, ``run_offsets[P+1]`` int64 CUDA tensor, ``max_runs`` the largest run
+    count of one plane if the caller knows it (``coco_rle.pack_runs`` returns all three).  ``status[P]``
+    int32: 0 ok, 1 the runs overflow the image (the in-image part is decoded), 2 plane refused."""
+    lib = _lib.load()
+    run_offsets = _need_cuda("run_offsets", run_offsets, torch.int64)
+    run_counts = _need_cuda("run_counts", run_counts)
+    if run_counts.dtype not in (torch.int32, torch.uint32):
+        raise TypeError(f"run_counts must be int32 / uint32 (holding unsigned 32-bit values), got {run_counts.dtype}")
+    planes = run_offsets.numel() - 1
+    if planes <= 0:
+        raise ValueError("run_offsets must hold at least two entries")
+    chunks, words = scan_layout(H, W)
+    dev = run_offsets.device
+    bits = torch.empty((planes, words), dtype=torch.int32, device=dev)
+    cc = torch.empty((planes, chunks), dtype=torch.int32, device=dev)
+    status = torch.empty((planes,), dtype=torch.int32, device=dev)
+    # scratch for planes whose run ends do not fit the shared-memory copy announced by max_runs
+    ends_ws = torch.empty((max(run_counts.numel(), 1),), dtype=torch.int32, device=dev)
+    counts_ptr = _ptr(run_counts) if run_counts.numel() else _ptr(ends_ws)      # never dereferenced when empty
+    with torch.cuda.device(dev):
+        rc = lib.la3d_rle_decode(counts_ptr, _ptr(run_offsets), planes, H, W, int(max_runs), _ptr(ends_ws), _ptr(bits),
+                                 _ptr(cc), _ptr(status), _stream())
+    _lib.check(rc, "la3d_rle_decode")
+    return bits, cc, status
+
+
+def unpack_bits(bits, H, W):
+    """Bit planes ``[P, words]`` -> NumPy ``bool [P,H,W]`` on the host (1/8 of the bytes cross the bus)."""
+    host = bits.detach().cpu().numpy().view(np.uint8)
+    P = host.shape[0]
+    return np.unpackbits(host, axis=1, bitorder="little")[:, :H * W].reshape(P, H, W).astype(bool)
+
+
 STAT_AREA, STAT_TOP, STAT_BOTTOM, STAT_LEFT, STAT_RIGHT, STAT_FIRST_ROW, STAT_LAST_ROW, STAT_ROWS = range(8)
 
 
@@ -408,6 +445,84 @@ def fit_boxes(depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, i
     B, I, H, W = masks.shape
     return BoxFitter(B, I, H, W, device=depth.device, out_dtype=out_dtype)(
         depth, K, masks, ground, method, yaw_steps, seed, image_offset).clone()
+
+
+def fit_boxes_bits(depth, K, bits, chunk_counts, I, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0,
+                   out_dtype=torch.float64):
+    """:func:`fit_boxes` from bit planes that already exist (``la3d_fit_boxes_bits``): the output of
+    :func:`rle_decode` or of an earlier :func:`mask_scan`.  ``bits[B*I, words]``, ``chunk_counts[B*I, chunks]``."""
+    lib = _lib.load()
+    depth = _need_cuda("depth", depth, torch.float32, pinned_ok=True)
+    K = _need_cuda("K", K, torch.float64)
+    bits = _need_cuda("bits", bits, torch.int32)
+    cc = _need_cuda("chunk_counts", chunk_counts, torch.int32)
+    B, H, W = depth.shape
+    chunks, words = scan_layout(H, W)
+    if tuple(bits.shape) != (B * I, words) or tuple(cc.shape) != (B * I, chunks) or tuple(K.shape) != (B, 3, 3):
+        raise ValueError("bit planes / chunk counts / K do not match depth and I")
+    if ground is not None:
+        ground = _need_cuda("ground", ground, torch.float64)
+        if tuple(ground.shape) != (B, I, 3):
+            raise ValueError(f"ground must be [{B},{I},3]")
+    dev = bits.device
+    ws_bytes = int(lib.la3d_fit_bits_workspace_bytes(B, I))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rec = torch.empty((B, I, REC), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.la3d_fit_boxes_bits(_ptr(depth), _ptr(bits), _ptr(cc), _ptr(K), _ptr(ground), B, I, H, W, _method_id(method),
+                                     int(yaw_steps), int(seed) & 0xFFFFFFFF, int(image_offset) & 0xFFFFFFFF, _ptr(ws),
+                                     ws_bytes, _ptr(rec), int(out_dtype == torch.float64), _stream())
+    _lib.check(rc, "la3d_fit_boxes_bits")
+    return rec
+
+
+class RleBoxFitter:
+    """``BoxFitter`` for masks given as COCO run-length annotations (``la3d_fit_boxes_rle``): one call =
+    three launches (decode with the preparation riding in its grid, subsample ranks, fit); the byte masks
+    never exist.  ``total_runs`` / ``max_runs``: capacity of the run arrays the plan will be called with."""
+
+    def __init__(self, B, I, H, W, total_runs, max_runs, device="cuda", out_dtype=torch.float64):
+        self.lib = _lib.load()
+        self.shape = (int(B), int(I), int(H), int(W))
+        self.device = torch.device(device)
+        if out_dtype not in (torch.float32, torch.float64):
+            raise TypeError("out_dtype must be float32 or float64")
+        self.out_dtype = out_dtype
+        self.max_runs = int(max_runs)
+        self.ws_bytes = int(self.lib.la3d_fit_workspace_bytes(*self.shape))
+        self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self.ends_ws = torch.empty((max(int(total_runs), 1),), dtype=torch.int32, device=self.device)
+        self.rle_status = torch.zeros((B * I,), dtype=torch.int32, device=self.device)
+        self.records = torch.empty((B, I, REC), dtype=out_dtype, device=self.device)
+
+    def __call__(self, depth, K, run_counts, run_offsets, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0,
+                 out=None):
+        """Returns ``records[B,I,64]``; ``self.rle_status[B*I]`` holds the decoder's per-plane status."""
+        B, I, H, W = self.shape
+        depth = _need_cuda("depth", depth, torch.float32, pinned_ok=True)
+        K = _need_cuda("K", K, torch.float64)
+        run_offsets = _need_cuda("run_offsets", run_offsets, torch.int64)
+        run_counts = _need_cuda("run_counts", run_counts)
+        if run_counts.dtype not in (torch.int32, torch.uint32):
+            raise TypeError("run_counts must be int32 / uint32")
+        if tuple(depth.shape) != (B, H, W) or tuple(K.shape) != (B, 3, 3) or run_offsets.numel() != B * I + 1:
+            raise ValueError(f"shapes do not match the plan {self.shape}")
+        if run_counts.numel() > self.ends_ws.numel():
+            raise ValueError("more runs than the plan was sized for (total_runs)")
+        if ground is not None:
+            ground = _need_cuda("ground", ground, torch.float64)
+            if tuple(ground.shape) != (B, I, 3):
+                raise ValueError(f"ground must be [{B},{I},3]")
+        rec = self.records if out is None else _need_cuda("out", out, self.out_dtype)
+        counts_ptr = _ptr(run_counts) if run_counts.numel() else _ptr(self.ends_ws)
+        with torch.cuda.device(self.device):
+            rc = self.lib.la3d_fit_boxes_rle(_ptr(depth), counts_ptr, _ptr(run_offsets), self.max_runs, _ptr(self.ends_ws),
+                                             _ptr(K), _ptr(ground), B, I, H, W, _method_id(method), int(yaw_steps),
+                                             int(seed) & 0xFFFFFFFF, int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace),
+                                             self.ws_bytes, _ptr(self.rle_status), _ptr(rec),
+                                             int(self.out_dtype == torch.float64), _stream())
+        _lib.check(rc, "la3d_fit_boxes_rle")
+        return rec
 
 
 def fit_points(points, offsets, sample_idx=None, K=None, ground=None, method="pca", yaw_steps=0,

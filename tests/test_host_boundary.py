@@ -68,6 +68,9 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
         "la3d_project_points": lambda: lib.la3d_project_points(None, None, None, 1, None, None),
         "la3d_iou_matrix": lambda: lib.la3d_iou_matrix(None, None, None, None, None, 1, None, None),
         "la3d_box2d_from_corners": lambda: lib.la3d_box2d_from_corners(None, None, None, None, 1, None, None, None),
+        "la3d_rle_decode": lambda: lib.la3d_rle_decode(None, None, 1, 4, 4, 0, None, None, None, None, None),
+        "la3d_fit_boxes_bits": lambda: lib.la3d_fit_boxes_bits(None, None, None, None, None, 1, 1, 4, 4, 0, 0, 0, 0, None, 0, None, 0, None),
+        "la3d_fit_boxes_rle": lambda: lib.la3d_fit_boxes_rle(None, None, None, 0, None, None, None, 1, 1, 4, 4, 0, 0, 0, 0, None, 0, None, None, 0, None),
         "la3d_masked_ratio_median": lambda: lib.la3d_masked_ratio_median(None, None, None, None, 1, 1, 4, 4, None, None, None),
     }
     for name, call in calls.items():
@@ -165,6 +168,12 @@ def test_signatures_match_the_reference(dropin):
         (util, "depth_to_points"): "(depth, K=None, R=None, t=None)",
         (util, "project_to_2d"): "(point_3d, camera_matrix)",
         (util, "draw_cube"): "(scene_dir, is_ground=False)",
+        (util, "analyze_mask"): "(mask, image_size, scale_threshold=100, boundary_threshold=10)",
+        (util, "get_maximum_height"): "(binary_mask)",
+        (util, "read_bounding_boxes_segmentations"): "(annotations_path_or_list, image_size)",
+        (util, "create_boolean_mask_from_polygon"): "(image_shape, segmentation)",
+        (util, "replace_categories_with_supercategories"): "(category_ids, json_file_path=None)",
+        (util, "align_to_depth_match"): "(mask, depth_map, object_name, project_root, model)",
         (box, "normalize"): "(v)",
         (box, "rotate_y"): "(yaw)",
         (box, "rotation_matrix_from_vectors"): "(vec1, vec2)",
