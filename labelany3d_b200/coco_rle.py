@@ -56,6 +56,19 @@ def runs_of(segmentation):
     return runs, (h, w)
 
 
+def runs_from_mask(mask):
+    """Run lengths (``uint32``) of one ``[h,w]`` mask in COCO order (column-major, first run counts
+    zeros): the format of the reference's ``binary_mask_to_rle`` (``src/download_coconut.py:167-175``)."""
+    flat = np.asarray(mask).ravel(order="F") != 0
+    if flat.size == 0:
+        return np.zeros(0, dtype=np.uint32)
+    edges = np.concatenate(([0], np.flatnonzero(flat[1:] != flat[:-1]) + 1, [flat.size]))
+    runs = np.diff(edges)
+    if flat[0]:
+        runs = np.concatenate(([0], runs))
+    return runs.astype(np.uint32)
+
+
 def pack_runs(run_lists):
     """``(counts uint32[total], offsets int64[P+1], max_runs)`` for a list of run-length arrays."""
     sizes = np.array([len(r) for r in run_lists], dtype=np.int64)

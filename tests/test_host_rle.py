@@ -29,6 +29,12 @@ def test_string_parser_matches_the_hand_derived_vectors_and_the_oracle():
         coco_rle.counts_from_string(b"5P")                    # the last character announces another one
 
 
+def test_runs_from_mask_is_the_reference_encoding():
+    for name, mask in rle_cases.codec_masks():
+        assert coco_rle.runs_from_mask(mask).tolist() == orr.rle_encode_fast(mask)["counts"], name
+    assert coco_rle.runs_from_mask(np.zeros((0, 0), bool)).size == 0
+
+
 def test_runs_of_and_pack_runs():
     runs, size = coco_rle.runs_of({"size": [3, 4], "counts": "246"})
     assert runs.dtype == np.uint32 and runs.tolist() == [2, 4, 6] and size == (3, 4)
