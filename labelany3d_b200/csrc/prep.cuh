@@ -102,13 +102,20 @@ __device__ __forceinline__ void mt_next_block_warp(uint32_t* mt, uint32_t* out) 
 // lanes build the ground rotations; then the warp generates the image's first pv.nblk blocks of
 // tempered words and saves the state.  Latency-bound on purpose: these warps ride in the launch of
 // the HBM-bound mask scan and should take as few of its slots as possible.
-template <int kT>
-__device__ __forceinline__ void prep_body(const PrepArgs& pa, int first) {
-  __shared__ uint32_t mt_all[kT / 32][kMtN];
+// kExtMt: the generator states live in caller-provided shared memory (`mt_ext`, kT/32 x 624 words) instead
+// of a static array, for host kernels whose other CTAs should not carry those 20 KB.
+template <int kT, bool kExtMt = false>
+__device__ __forceinline__ void prep_body(const PrepArgs& pa, int first, uint32_t* mt_ext = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = first + warp;
   if (b >= pa.B) return;                               // warp-uniform; no block barrier below
-  uint32_t* mt = mt_all[warp];
+  uint32_t* mt;
+  if constexpr (kExtMt) {
+    mt = mt_ext + warp * kMtN;
+  } else {
+    __shared__ uint32_t mt_all[kT / 32][kMtN];
+    mt = mt_all[warp];
+  }
   const PrepView& pv = pa.pv;
   if (lane == 0) {
     uint32_t s = pa.seed0 + (uint32_t)b;       // mod 2^32, as np.random.seed requires

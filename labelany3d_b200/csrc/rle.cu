@@ -11,14 +11,16 @@
 // COCO runs are COLUMN-major (pixel (y,x) has run position x*H + y), the bit planes are
 // row-major, so the kernel is a bit transposition:
 //   1. inclusive prefix sums of the plane's run lengths -> run ends E[] (shared memory);
-//   2. per band of 32 rows and strip of 32 columns: lane l owns column 32 s + l, finds the run
-//      holding its first pixel by binary search over E[], walks the (few) runs crossing its
-//      32 pixels into a 32-bit column word, and the warp transposes the 32x32 bit tile with
-//      five shuffle rounds (skipped when the tile is empty); rows go to a padded staging tile;
-//   3. a band of 32 rows is exactly W words of the plane's bit stream (32*W pixels), so the CTA
-//      re-packs the staged rows (funnel shifts when W is not a multiple of 32) into finished
-//      words, stores them coalesced, and adds their popcounts to the quarter counts
-//      (a segmented warp reduction, then one red.global per quarter and warp).
+//   2. per column the run that holds its top pixel (one binary search per column, so every later
+//      search stays inside one column's handful of runs), and the row / column range the set
+//      pixels can lie in (most of a plane is empty: those rows are written as zeros directly);
+//   3. a band of 32 rows is exactly W words of the plane's bit stream (32*W pixels) and belongs to one
+//      warp: per strip of 32 columns lane l owns column 32 s + l, walks the (few) runs crossing its 32
+//      pixels into a 32-bit column word, and the warp transposes the 32x32 bit tile with five shuffle
+//      rounds (skipped when the tile is empty) into its padded staging tile; it then re-packs the
+//      staged rows (funnel shifts when W is not a multiple of 32) into finished words, stores them
+//      coalesced, and adds their popcounts to the quarter counts (a segmented warp reduction,
+//      then one red.global per quarter).  No block barrier after the set-up.
 //
 // kPrep: like the mask scan, the first ceil(B/8) CTAs of the launch may instead run the
 // mask-independent preparation of the batch (prep.cuh), so la3d_fit_boxes_rle stays at three launches.
@@ -69,22 +71,33 @@ __device__ __forceinline__ uint32_t bit_range(uint32_t a, uint32_t b) {       //
   return hi & ~((1u << a) - 1u);
 }
 
+// number of run ends <= q among E[lo..hi), plus lo: run_of restricted to a column's runs
+__device__ __forceinline__ int run_of_in(const uint32_t* __restrict__ E, int lo, int hi, uint32_t q) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (E[mid] <= q) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 template <bool kPrep>
-__global__ void __launch_bounds__(kThreads) rle_decode_kernel(RleArgs a, PrepArgs pa) {
+__global__ void __launch_bounds__(kThreads, 6) rle_decode_kernel(RleArgs a, PrepArgs pa) {
   extern __shared__ __align__(16) uint32_t dyn[];
   __shared__ unsigned long long warp_tot[kWarps];
+  __shared__ int s_ylo[kWarps], s_yhi[kWarps];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int plane = blockIdx.x;
   if (kPrep) {
     const int prep_ctas = (pa.B + kWarps - 1) / kWarps;           // one warp per image
-    if (plane < prep_ctas) { prep_body<kThreads>(pa, plane * kWarps); return; }   // CTA-uniform
+    if (plane < prep_ctas) { prep_body<kThreads, true>(pa, plane * kWarps, dyn); return; }   // CTA-uniform
     plane -= prep_ctas;
   }
   const int H = a.H, W = a.W, HW = a.HW;
   const int pitch = (W + 31) >> 5;               // 32-column strips per row
   const int P = pitch | 1;                       // staging pitch: odd, so a tile's 32 rows hit 32 banks
-  uint32_t* stage = dyn;                         // [32][P]
-  uint32_t* ends_smem = dyn + 32 * P;            // [smem_runs]
+  uint32_t* stage = dyn + (size_t)warp * 32 * P; // [kWarps][32][P]: every warp stages its own band
+  int* col_run = reinterpret_cast<int*>(dyn + (size_t)kWarps * 32 * P);     // [W+1] run holding the top pixel of a column
+  uint32_t* ends_smem = dyn + (size_t)kWarps * 32 * P + (W + 1);            // [smem_runs]
 
   const long long r0 = a.offsets[plane];
   const long long m_ll = a.offsets[plane + 1] - r0;
@@ -126,28 +139,56 @@ __global__ void __launch_bounds__(kThreads) rle_decode_kernel(RleArgs a, PrepArg
   for (int c = tid; c < a.chunks; c += kThreads) cc[c] = 0u;
   __syncthreads();
 
-  // columns that can hold a set pixel: from the first 1-run's start to the last 1-run's end
+  // ---- 2. where the set pixels can be: per column the run that holds its top pixel (all later searches
+  // stay inside one column's runs), the column range, and the row range (a 1-run that crosses into the
+  // next column touches the last and the first row)
+  for (int x = tid; x < W; x += kThreads) col_run[x] = run_of(E, m, (uint32_t)x * (uint32_t)H);
+  if (tid == 0) col_run[W] = m;
+  int y_lo = H, y_hi = -1;
+  for (int j = 1 + 2 * tid; j < m; j += 2 * kThreads) {
+    const uint32_t s0 = E[j - 1], e0 = min(E[j], (uint32_t)HW);
+    if (e0 > s0) {
+      const uint32_t cs = s0 / (uint32_t)H, ce = (e0 - 1u) / (uint32_t)H;
+      if (cs != ce) { y_lo = 0; y_hi = H - 1; }
+      else { y_lo = min(y_lo, (int)(s0 - cs * (uint32_t)H)); y_hi = max(y_hi, (int)(e0 - 1u - cs * (uint32_t)H)); }
+    }
+  }
+  y_lo = __reduce_min_sync(kFull, y_lo);
+  y_hi = __reduce_max_sync(kFull, y_hi);
+  if (lane == 0) { s_ylo[warp] = y_lo; s_yhi[warp] = y_hi; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) { y_lo = min(y_lo, s_ylo[w]); y_hi = max(y_hi, s_yhi[w]); }
   int x_lo = W, x_hi = -1;
-  if (m >= 2) {
+  if (m >= 2 && y_hi >= y_lo) {
     const uint32_t first = E[0];
     const uint32_t last = min((m & 1) ? E[m - 2] : E[m - 1], (uint32_t)HW);
     if (last > first) { x_lo = (int)(first / (uint32_t)H); x_hi = (int)((last - 1u) / (uint32_t)H); }
   }
+  const int s_lo = x_lo >> 5, s_hi = x_hi >> 5;  // strips that can hold a set pixel (none if x_hi < x_lo)
 
-  // ---- 2./3. bands of 32 rows = W words of the bit stream each ----
+  // ---- 3. bands of 32 rows = W words of the bit stream each; a warp owns whole bands ----
   const long long words_total = (long long)a.chunks * kChunkWords;
   uint32_t* out_bits = a.bits + (size_t)plane * words_total;
   const bool aligned = (W & 31) == 0;
-  for (long long w_base = 0; w_base < words_total; w_base += W) {
-    const long long y0_ll = (w_base / W) * 32;
+  const int n_bands = (int)((words_total + W - 1) / W);
+  for (int band = warp; band < n_bands; band += kWarps) {
+    const long long w_base = (long long)band * W;
+    const int n_words = (int)min((long long)W, words_total - w_base);
+    const long long y0_ll = (long long)band * 32;
     const int nrows = y0_ll >= H ? 0 : min(32, H - (int)y0_ll);
     const int y0 = (int)min(y0_ll, (long long)H);
-    for (int s = warp; s < pitch; s += kWarps) {
+    if (nrows == 0 || x_hi < x_lo || y0 > y_hi || y0 + nrows - 1 < y_lo) {   // nothing set in these rows
+      for (int wi = lane; wi < n_words; wi += 32) out_bits[w_base + wi] = 0u;
+      continue;
+    }
+    for (int s = s_lo; s <= s_hi; ++s) {
       const int x = 32 * s + lane;
       uint32_t word = 0;
-      if (nrows > 0 && x < W && x >= x_lo && x <= x_hi) {
+      if (x < W) {
+        const int k_top = col_run[x], k_next = col_run[x + 1];
         const uint32_t q0 = (uint32_t)x * (uint32_t)H + (uint32_t)y0, q1 = q0 + (uint32_t)nrows;
-        int k = run_of(E, m, q0);
+        int k = run_of_in(E, k_top, k_next, q0);
         uint32_t pos = q0;
         while (pos < q1 && k < m) {
           const uint32_t e = E[k];
@@ -160,16 +201,15 @@ __global__ void __launch_bounds__(kThreads) rle_decode_kernel(RleArgs a, PrepArg
       if (__any_sync(kFull, word != 0u)) word = transpose32(word, lane);      // now lane = row, bit = column
       stage[lane * P + s] = word;
     }
-    __syncthreads();
-    const int n_words = (int)min((long long)W, words_total - w_base);
-    for (int base_w = warp * 32; base_w < n_words; base_w += kThreads) {      // warp-uniform trip count
+    __syncwarp();
+    for (int base_w = 0; base_w < n_words; base_w += 32) {                    // warp-uniform trip count
       const int wi = base_w + lane;
       const bool active = wi < n_words;
       uint32_t out = 0;
       if (active) {
         if (aligned) {
-          const int r = wi / pitch;
-          out = stage[r * P + (wi - r * pitch)];
+          const int r = wi / pitch, c = wi - r * pitch;
+          if (c >= s_lo && c <= s_hi) out = stage[r * P + c];
         } else {
           const uint32_t p = 32u * (uint32_t)wi;
           int r = (int)(p / (uint32_t)W);
@@ -178,8 +218,8 @@ __global__ void __launch_bounds__(kThreads) rle_decode_kernel(RleArgs a, PrepArg
           while (got < 32 && r < 32) {
             const int n = min(32 - got, W - x);
             const int c = x >> 5;
-            const uint32_t w0 = stage[r * P + c];
-            const uint32_t w1 = (c + 1 < pitch) ? stage[r * P + c + 1] : 0u;
+            const uint32_t w0 = (c >= s_lo && c <= s_hi) ? stage[r * P + c] : 0u;
+            const uint32_t w1 = (c + 1 >= s_lo && c + 1 <= s_hi) ? stage[r * P + c + 1] : 0u;
             uint32_t v = __funnelshift_r(w0, w1, x & 31);
             if (n < 32) v &= (1u << n) - 1u;
             out |= v << got;
@@ -188,6 +228,7 @@ __global__ void __launch_bounds__(kThreads) rle_decode_kernel(RleArgs a, PrepArg
         }
         out_bits[w_base + wi] = out;
       }
+      if (!__any_sync(kFull, out != 0u)) continue;                            // warp-uniform
       // quarter counts: lanes of one 4-word quarter are neighbours; sum them, one red per quarter
       const long long wg = w_base + wi;
       const uint32_t key = active ? (uint32_t)(wg >> 2) : (0x80000000u | (uint32_t)lane);
@@ -200,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) rle_decode_kernel(RleArgs a, PrepArg
       const bool head = lane == 0 || kp != key;
       if (active && head && v) atomicAdd(&cc[wg >> 4], v << (8 * (int)((wg >> 2) & 3)));
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -213,21 +254,24 @@ int launch_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes
   LA3D_REQUIRE(counts && offsets && bits && chunk_counts && status, "null pointer");
   LA3D_REQUIRE(planes > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
-  LA3D_REQUIRE(W <= 32768, "image wider than 32768 pixels");
+  LA3D_REQUIRE(W <= 4096, "image wider than 4096 pixels");
   LA3D_REQUIRE(max_runs >= 0, "negative max_runs");
   static_assert(sizeof(long long) == sizeof(int64_t), "offsets are 64-bit");
   RleArgs a{};
   a.counts = counts; a.offsets = reinterpret_cast<const long long*>(offsets); a.ends_ws = ends_ws;
   a.H = H; a.W = W; a.HW = H * W; a.chunks = (int)la3d_chunks_per_plane(H, W);
-  a.smem_runs = max_runs > kMaxSmemRuns ? 0 : max_runs;      // too many for shared memory: every plane uses ends_ws
+  a.bits = bits; a.chunk_counts = chunk_counts; a.status = status;
+  // shared memory: a staging tile per warp, the per-column run table, and the run ends if they fit beside them
+  const int P = ((W + 31) >> 5) | 1;
+  const size_t fixed = ((size_t)kWarps * 32 * P + (size_t)W + 1) * 4;
+  const size_t budget = 200 * 1024;
+  a.smem_runs = (max_runs <= kMaxSmemRuns && fixed + (size_t)max_runs * 4 <= budget) ? max_runs : 0;
   if (a.smem_runs == 0 && !ends_ws && max_runs > 0) {
-    set_error("la3d_rle_decode: %d runs per plane need the ends_ws workspace (more than %d)", max_runs, kMaxSmemRuns);
+    set_error("la3d_rle_decode: %d runs per plane do not fit shared memory; pass the ends_ws workspace", max_runs);
     return LA3D_EINVAL;
   }
-  a.bits = bits; a.chunk_counts = chunk_counts; a.status = status;
-  const int P = ((W + 31) >> 5) | 1;
-  const size_t smem = ((size_t)32 * P + (size_t)a.smem_runs) * 4;
-  LA3D_REQUIRE(smem <= 200 * 1024, "image too wide for the staging tile plus the run ends in shared memory");
+  size_t smem = fixed + (size_t)a.smem_runs * 4;
+  if (prep && smem < (size_t)kWarps * kMtN * 4) smem = (size_t)kWarps * kMtN * 4;      // the preparation CTAs' generator states
   const long long ctas = (long long)planes + (prep ? (prep->B + kWarps - 1) / kWarps : 0);
   LA3D_REQUIRE(ctas < (1ll << 31), "grid too large");
   const PrepArgs pa = prep ? *prep : PrepArgs{};
