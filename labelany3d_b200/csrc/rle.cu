@@ -24,6 +24,8 @@
 //
 // kPrep: like the mask scan, the first ceil(B/8) CTAs of the launch may instead run the
 // mask-independent preparation of the batch (prep.cuh), so la3d_fit_boxes_rle stays at three launches.
+#include <cstdlib>
+
 #include "prep.cuh"
 
 namespace la3d {
@@ -80,8 +82,8 @@ __device__ __forceinline__ int run_of_in(const uint32_t* __restrict__ E, int lo,
   return lo;
 }
 
-template <bool kPrep>
-__global__ void __launch_bounds__(kThreads, 6) rle_decode_kernel(RleArgs a, PrepArgs pa) {
+template <bool kPrep, int kMinCtas>
+__global__ void __launch_bounds__(kThreads, kMinCtas) rle_decode_kernel(RleArgs a, PrepArgs pa) {
   extern __shared__ __align__(16) uint32_t dyn[];
   __shared__ unsigned long long warp_tot[kWarps];
   __shared__ int s_ylo[kWarps], s_yhi[kWarps];
@@ -202,15 +204,38 @@ __global__ void __launch_bounds__(kThreads, 6) rle_decode_kernel(RleArgs a, Prep
       stage[lane * P + s] = word;
     }
     __syncwarp();
-    for (int base_w = 0; base_w < n_words; base_w += 32) {                    // warp-uniform trip count
-      const int wi = base_w + lane;
-      const bool active = wi < n_words;
-      uint32_t out = 0;
-      if (active) {
-        if (aligned) {
-          const int r = wi / pitch, c = wi - r * pitch;
-          if (c >= s_lo && c <= s_hi) out = stage[r * P + c];
-        } else {
+    // quarter counts of the finished words a warp instruction holds: lanes of one 4-word quarter are
+    // neighbours; sum them (segmented shuffle reduction), one red per quarter
+    auto count_words = [&](uint32_t out, bool active, long long wg) {
+      const uint32_t key = active ? (uint32_t)(wg >> 2) : (0x80000000u | (uint32_t)lane);
+      uint32_t v = __popc(out);
+      const uint32_t k1 = __shfl_down_sync(kFull, key, 1), v1 = __shfl_down_sync(kFull, v, 1);
+      if (lane + 1 < 32 && k1 == key) v += v1;
+      const uint32_t k2 = __shfl_down_sync(kFull, key, 2), v2 = __shfl_down_sync(kFull, v, 2);
+      if (lane + 2 < 32 && k2 == key) v += v2;
+      const uint32_t kp = __shfl_up_sync(kFull, key, 1);
+      const bool head = lane == 0 || kp != key;
+      if (active && head && v) atomicAdd(&cc[wg >> 4], v << (8 * (int)((wg >> 2) & 3)));
+    };
+    if (aligned) {
+      // a row is `pitch` whole words: row by row, no division; only rows and strips in range read the tile
+      for (int r = 0; r < 32 && r * pitch < n_words; ++r) {
+        const bool row_live = r < nrows && y0 + r >= y_lo && y0 + r <= y_hi;
+        const long long row_w = w_base + (long long)r * pitch;
+        for (int c0 = 0; c0 < pitch; c0 += 32) {                              // warp-uniform trip count
+          const int c = c0 + lane;
+          const bool active = c < pitch && r * pitch + c < n_words;
+          const uint32_t out = (active && row_live && c >= s_lo && c <= s_hi) ? stage[r * P + c] : 0u;
+          if (active) out_bits[row_w + c] = out;
+          if (__any_sync(kFull, out != 0u)) count_words(out, active, row_w + c);
+        }
+      }
+    } else {
+      for (int base_w = 0; base_w < n_words; base_w += 32) {                  // warp-uniform trip count
+        const int wi = base_w + lane;
+        const bool active = wi < n_words;
+        uint32_t out = 0;
+        if (active) {
           const uint32_t p = 32u * (uint32_t)wi;
           int r = (int)(p / (uint32_t)W);
           int x = (int)(p - (uint32_t)r * (uint32_t)W);
@@ -225,21 +250,10 @@ __global__ void __launch_bounds__(kThreads, 6) rle_decode_kernel(RleArgs a, Prep
             out |= v << got;
             got += n; ++r; x = 0;
           }
+          out_bits[w_base + wi] = out;
         }
-        out_bits[w_base + wi] = out;
+        if (__any_sync(kFull, out != 0u)) count_words(out, active, w_base + wi);
       }
-      if (!__any_sync(kFull, out != 0u)) continue;                            // warp-uniform
-      // quarter counts: lanes of one 4-word quarter are neighbours; sum them, one red per quarter
-      const long long wg = w_base + wi;
-      const uint32_t key = active ? (uint32_t)(wg >> 2) : (0x80000000u | (uint32_t)lane);
-      uint32_t v = __popc(out);
-      const uint32_t k1 = __shfl_down_sync(kFull, key, 1), v1 = __shfl_down_sync(kFull, v, 1);
-      if (lane + 1 < 32 && k1 == key) v += v1;
-      const uint32_t k2 = __shfl_down_sync(kFull, key, 2), v2 = __shfl_down_sync(kFull, v, 2);
-      if (lane + 2 < 32 && k2 == key) v += v2;
-      const uint32_t kp = __shfl_up_sync(kFull, key, 1);
-      const bool head = lane == 0 || kp != key;
-      if (active && head && v) atomicAdd(&cc[wg >> 4], v << (8 * (int)((wg >> 2) & 3)));
     }
     __syncwarp();
   }
@@ -275,15 +289,23 @@ int launch_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes
   const long long ctas = (long long)planes + (prep ? (prep->B + kWarps - 1) / kWarps : 0);
   LA3D_REQUIRE(ctas < (1ll << 31), "grid too large");
   const PrepArgs pa = prep ? *prep : PrepArgs{};
-  // opt in to more dynamic shared memory only when a launch needs more than any before it
-  static size_t opted[2] = {16 * 1024, 16 * 1024};
-  if (smem > opted[prep ? 1 : 0]) {
-    if (prep) LA3D_CUDA(cudaFuncSetAttribute(rle_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else LA3D_CUDA(cudaFuncSetAttribute(rle_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    opted[prep ? 1 : 0] = smem;
-  }
-  if (prep) rle_decode_kernel<true><<<(unsigned)ctas, kThreads, smem, s>>>(a, pa);
-  else rle_decode_kernel<false><<<(unsigned)ctas, kThreads, smem, s>>>(a, pa);
+  // LA3D_RLE_VARIANT=1: compile-time bound of 6 resident CTAs per SM (40 registers, spills) instead of 5 (tuning knob)
+  const char* env = getenv("LA3D_RLE_VARIANT");
+  const int variant = env ? atoi(env) : 0;
+  auto launch = [&](auto kernel, int slot) -> int {
+    // opt in to more dynamic shared memory only when a launch needs more than any before it
+    static size_t opted[4] = {16 * 1024, 16 * 1024, 16 * 1024, 16 * 1024};
+    if (smem > opted[slot]) {
+      LA3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      opted[slot] = smem;
+    }
+    kernel<<<(unsigned)ctas, kThreads, smem, s>>>(a, pa);
+    return LA3D_OK;
+  };
+  int rc;
+  if (variant == 1) rc = prep ? launch(rle_decode_kernel<true, 6>, 0) : launch(rle_decode_kernel<false, 6>, 1);
+  else rc = prep ? launch(rle_decode_kernel<true, 5>, 2) : launch(rle_decode_kernel<false, 5>, 3);
+  if (rc) return rc;
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
 }
