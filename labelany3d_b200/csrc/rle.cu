@@ -17,10 +17,12 @@
 //   3. a band of 32 rows is exactly W words of the plane's bit stream (32*W pixels) and belongs to one
 //      warp: per strip of 32 columns lane l owns column 32 s + l, walks the (few) runs crossing its 32
 //      pixels into a 32-bit column word, and the warp transposes the 32x32 bit tile with five shuffle
-//      rounds (skipped when the tile is empty) into its padded staging tile; it then re-packs the
-//      staged rows (funnel shifts when W is not a multiple of 32) into finished words, stores them
-//      coalesced, and adds their popcounts to the quarter counts (a segmented warp reduction,
-//      then one red.global per quarter).  No block barrier after the set-up.
+//      rounds (skipped when the tile is empty).  W % 128 == 0 (640, 1536, ...): rows are whole words and
+//      quarters four strips of a row, so each lane stores its row's word straight from the register over
+//      the zeroed band and accumulates its quarter's popcount (one red.global per non-empty quarter).
+//      Any other W: the tiles go to a padded staging tile, the warp re-packs the staged rows with funnel
+//      shifts into finished words, stores them coalesced and reduces their popcounts per quarter with a
+//      segmented shuffle reduction.  No block barrier after the set-up.
 //
 // kPrep: like the mask scan, the first ceil(B/8) CTAs of the launch may instead run the
 // mask-independent preparation of the batch (prep.cuh), so la3d_fit_boxes_rle stays at three launches.
@@ -40,7 +42,8 @@ struct RleArgs {
   const uint32_t* counts;      // run lengths of all planes, back to back
   const long long* offsets;    // [planes+1] first run of every plane
   uint32_t* ends_ws;           // nullable [total runs]: run ends of planes that do not fit shared memory
-  int H, W, HW, chunks, smem_runs;
+  int H, W, HW, chunks, smem_runs, stage_words;   // stage_words: staging tile per warp (0 on the fast path)
+  int fast;                    // W % 128 == 0 and 16-byte aligned bit planes: rows and quarters never straddle words
   uint32_t* bits;
   uint32_t* chunk_counts;
   int32_t* status;
@@ -97,9 +100,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) rle_decode_kernel(RleArgs 
   const int H = a.H, W = a.W, HW = a.HW;
   const int pitch = (W + 31) >> 5;               // 32-column strips per row
   const int P = pitch | 1;                       // staging pitch: odd, so a tile's 32 rows hit 32 banks
-  uint32_t* stage = dyn + (size_t)warp * 32 * P; // [kWarps][32][P]: every warp stages its own band
-  int* col_run = reinterpret_cast<int*>(dyn + (size_t)kWarps * 32 * P);     // [W+1] run holding the top pixel of a column
-  uint32_t* ends_smem = dyn + (size_t)kWarps * 32 * P + (W + 1);            // [smem_runs]
+  uint32_t* stage = dyn + (size_t)warp * a.stage_words;                     // [kWarps][32][P]: every warp stages its own band
+  int* col_run = reinterpret_cast<int*>(dyn + (size_t)kWarps * a.stage_words);   // [W+1] run holding the top pixel of a column
+  uint32_t* ends_smem = dyn + (size_t)kWarps * a.stage_words + (W + 1);     // [smem_runs]
 
   const long long r0 = a.offsets[plane];
   const long long m_ll = a.offsets[plane + 1] - r0;
@@ -172,7 +175,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) rle_decode_kernel(RleArgs 
   // ---- 3. bands of 32 rows = W words of the bit stream each; a warp owns whole bands ----
   const long long words_total = (long long)a.chunks * kChunkWords;
   uint32_t* out_bits = a.bits + (size_t)plane * words_total;
-  const bool aligned = (W & 31) == 0;
   const int n_bands = (int)((words_total + W - 1) / W);
   for (int band = warp; band < n_bands; band += kWarps) {
     const long long w_base = (long long)band * W;
@@ -181,10 +183,17 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) rle_decode_kernel(RleArgs 
     const int nrows = y0_ll >= H ? 0 : min(32, H - (int)y0_ll);
     const int y0 = (int)min(y0_ll, (long long)H);
     if (nrows == 0 || x_hi < x_lo || y0 > y_hi || y0 + nrows - 1 < y_lo) {   // nothing set in these rows
-      for (int wi = lane; wi < n_words; wi += 32) out_bits[w_base + wi] = 0u;
+      if (a.fast) {
+        uint4* z = reinterpret_cast<uint4*>(out_bits + w_base);
+        for (int i = lane; i < (n_words >> 2); i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        for (int wi = lane; wi < n_words; wi += 32) out_bits[w_base + wi] = 0u;
+      }
       continue;
     }
-    for (int s = s_lo; s <= s_hi; ++s) {
+    // one 32x32 tile: lane l owns column 32 s + l, walks the runs crossing its rows of the band into a
+    // column word, and the warp transposes the tile (skipped when empty): lane = row, bit = column
+    auto tile = [&](int s) -> uint32_t {
       const int x = 32 * s + lane;
       uint32_t word = 0;
       if (x < W) {
@@ -200,13 +209,56 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) rle_decode_kernel(RleArgs 
           if (e <= q1) ++k;
         }
       }
-      if (__any_sync(kFull, word != 0u)) word = transpose32(word, lane);      // now lane = row, bit = column
-      stage[lane * P + s] = word;
+      if (__any_sync(kFull, word != 0u)) word = transpose32(word, lane);
+      return word;
+    };
+    if (a.fast) {
+      // W % 128 == 0: a row is `pitch` whole words and a quarter is four strips of one row.  Zero the band with
+      // 16-byte stores, then every lane stores its row's word of each tile straight from the register and
+      // keeps the popcount of the quarter it is in; no staging, no shuffles for the counts.
+      uint4* z = reinterpret_cast<uint4*>(out_bits + w_base);
+      for (int i = lane; i < (n_words >> 2); i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      __syncwarp();                                       // orders the zeros before the other lanes' words below
+      uint32_t acc = 0;
+      for (int s = s_lo; s <= s_hi; ++s) {
+        const uint32_t word = tile(s);
+        const long long wg = w_base + (long long)lane * pitch + s;
+        if (word) out_bits[wg] = word;                    // rows past the image hold no bits and are never stored
+        acc += __popc(word);
+        if ((s & 3) == 3 || s == s_hi) {
+          if (acc) atomicAdd(&cc[wg >> 4], acc << (8 * (int)((wg >> 2) & 3)));
+          acc = 0;
+        }
+      }
+      continue;
     }
+    for (int s = s_lo; s <= s_hi; ++s) stage[lane * P + s] = tile(s);
     __syncwarp();
-    // quarter counts of the finished words a warp instruction holds: lanes of one 4-word quarter are
-    // neighbours; sum them (segmented shuffle reduction), one red per quarter
-    auto count_words = [&](uint32_t out, bool active, long long wg) {
+    for (int base_w = 0; base_w < n_words; base_w += 32) {                    // warp-uniform trip count
+      const int wi = base_w + lane;
+      const bool active = wi < n_words;
+      uint32_t out = 0;
+      if (active) {
+        const uint32_t p = 32u * (uint32_t)wi;
+        int r = (int)(p / (uint32_t)W);
+        int x = (int)(p - (uint32_t)r * (uint32_t)W);
+        int got = 0;
+        while (got < 32 && r < 32) {
+          const int n = min(32 - got, W - x);
+          const int c = x >> 5;
+          const uint32_t w0 = (c >= s_lo && c <= s_hi) ? stage[r * P + c] : 0u;
+          const uint32_t w1 = (c + 1 >= s_lo && c + 1 <= s_hi) ? stage[r * P + c + 1] : 0u;
+          uint32_t v = __funnelshift_r(w0, w1, x & 31);
+          if (n < 32) v &= (1u << n) - 1u;
+          out |= v << got;
+          got += n; ++r; x = 0;
+        }
+        out_bits[w_base + wi] = out;
+      }
+      if (!__any_sync(kFull, out != 0u)) continue;                            // warp-uniform
+      // quarter counts: lanes of one 4-word quarter are neighbours; sum them (segmented shuffle
+      // reduction), one red per quarter
+      const long long wg = w_base + wi;
       const uint32_t key = active ? (uint32_t)(wg >> 2) : (0x80000000u | (uint32_t)lane);
       uint32_t v = __popc(out);
       const uint32_t k1 = __shfl_down_sync(kFull, key, 1), v1 = __shfl_down_sync(kFull, v, 1);
@@ -216,44 +268,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) rle_decode_kernel(RleArgs 
       const uint32_t kp = __shfl_up_sync(kFull, key, 1);
       const bool head = lane == 0 || kp != key;
       if (active && head && v) atomicAdd(&cc[wg >> 4], v << (8 * (int)((wg >> 2) & 3)));
-    };
-    if (aligned) {
-      // a row is `pitch` whole words: row by row, no division; only rows and strips in range read the tile
-      for (int r = 0; r < 32 && r * pitch < n_words; ++r) {
-        const bool row_live = r < nrows && y0 + r >= y_lo && y0 + r <= y_hi;
-        const long long row_w = w_base + (long long)r * pitch;
-        for (int c0 = 0; c0 < pitch; c0 += 32) {                              // warp-uniform trip count
-          const int c = c0 + lane;
-          const bool active = c < pitch && r * pitch + c < n_words;
-          const uint32_t out = (active && row_live && c >= s_lo && c <= s_hi) ? stage[r * P + c] : 0u;
-          if (active) out_bits[row_w + c] = out;
-          if (__any_sync(kFull, out != 0u)) count_words(out, active, row_w + c);
-        }
-      }
-    } else {
-      for (int base_w = 0; base_w < n_words; base_w += 32) {                  // warp-uniform trip count
-        const int wi = base_w + lane;
-        const bool active = wi < n_words;
-        uint32_t out = 0;
-        if (active) {
-          const uint32_t p = 32u * (uint32_t)wi;
-          int r = (int)(p / (uint32_t)W);
-          int x = (int)(p - (uint32_t)r * (uint32_t)W);
-          int got = 0;
-          while (got < 32 && r < 32) {
-            const int n = min(32 - got, W - x);
-            const int c = x >> 5;
-            const uint32_t w0 = (c >= s_lo && c <= s_hi) ? stage[r * P + c] : 0u;
-            const uint32_t w1 = (c + 1 >= s_lo && c + 1 <= s_hi) ? stage[r * P + c + 1] : 0u;
-            uint32_t v = __funnelshift_r(w0, w1, x & 31);
-            if (n < 32) v &= (1u << n) - 1u;
-            out |= v << got;
-            got += n; ++r; x = 0;
-          }
-          out_bits[w_base + wi] = out;
-        }
-        if (__any_sync(kFull, out != 0u)) count_words(out, active, w_base + wi);
-      }
     }
     __syncwarp();
   }
@@ -275,9 +289,11 @@ int launch_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes
   a.counts = counts; a.offsets = reinterpret_cast<const long long*>(offsets); a.ends_ws = ends_ws;
   a.H = H; a.W = W; a.HW = H * W; a.chunks = (int)la3d_chunks_per_plane(H, W);
   a.bits = bits; a.chunk_counts = chunk_counts; a.status = status;
+  a.fast = (W % 128 == 0) && aligned16(bits);
   // shared memory: a staging tile per warp, the per-column run table, and the run ends if they fit beside them
   const int P = ((W + 31) >> 5) | 1;
-  const size_t fixed = ((size_t)kWarps * 32 * P + (size_t)W + 1) * 4;
+  a.stage_words = a.fast ? 0 : 32 * P;
+  const size_t fixed = ((size_t)kWarps * a.stage_words + (size_t)W + 1) * 4;
   const size_t budget = 200 * 1024;
   a.smem_runs = (max_runs <= kMaxSmemRuns && fixed + (size_t)max_runs * 4 <= budget) ? max_runs : 0;
   if (a.smem_runs == 0 && !ends_ws && max_runs > 0) {
