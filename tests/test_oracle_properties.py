@@ -70,3 +70,25 @@ def test_median_of_ratios_is_a_float32_order_statistic(seed, n):
     want = srt[n // 2] if n % 2 else np.float32(np.float32(srt[n // 2 - 1] + srt[n // 2]) / np.float32(2))
     got = np.median(r)
     assert got.dtype == np.float32 and got == want
+
+
+@FAST
+@given(seed=st.integers(0, 10**6), h=st.integers(1, 70), w=st.integers(1, 150), density=st.sampled_from([0.0, 0.02, 0.3, 0.5, 0.97, 1.0]))
+def test_run_length_codec_round_trips(seed, h, w, density):
+    """COCO run-length codec (oracle/la3d_oracle_rle.py) and the product's host-side helpers
+    (labelany3d_b200/coco_rle.py): encode -> decode is the identity, the compressed string survives a round
+    trip through both parsers, the run sum is h*w, and the device layout agrees with the decoded mask."""
+    from labelany3d_b200 import coco_rle
+    from oracle import la3d_oracle_rle as orr
+    rng = np.random.RandomState(seed)
+    mask = rng.rand(h, w) < density
+    counts = orr.rle_encode_fast(mask)["counts"]
+    assert counts == orr.rle_encode(mask.astype(np.uint8))["counts"] == coco_rle.runs_from_mask(mask).tolist()
+    assert sum(counts) == h * w and all(c > 0 for c in counts[1:])
+    assert np.array_equal(orr.rle_decode(counts, h, w).astype(bool), mask)
+    text = orr.rle_to_string(counts)
+    assert orr.rle_from_string(text) == counts == coco_rle.counts_from_string(text).tolist()
+    bits, cc, status = orr.rle_to_bits([counts], h, w)
+    flat = np.unpackbits(bits[0].view(np.uint8), bitorder="little").astype(bool)
+    assert status[0] == 0 and np.array_equal(flat[:h * w].reshape(h, w), mask) and not flat[h * w:].any()
+    assert int(cc[0].view(np.uint8).sum()) == int(mask.sum())
