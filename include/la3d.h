@@ -224,6 +224,23 @@ int la3d_fit_boxes_rle(const float* depth, const uint32_t* run_counts, const int
                        int32_t* rle_status, void* records, int rec_f64, la3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * The box from EVERY masked pixel: estimate_bbox (src/util_3dbox.py:106-178, method='pca') with the
+ * random 500-point draw of :123-125 replaced by the identity - deterministic, no generator involved.
+ * One CTA per box reduces the centroid / covariance sums of the ground-aligned footprint over all set
+ * pixels of the plane (float64, fixed summation order), takes the yaw from them (the closed form of
+ * scikit-learn's PCA(2)), reduces the extents at that yaw in a second sweep and writes the same record as
+ * la3d_fit_scanned (status codes included; LA3D_O_NVALID / LA3D_O_NMASK count all pixels).
+ *   la3d_fit_all_points: bits from la3d_mask_scan / la3d_rle_decode, prep from la3d_fit_prepare
+ *   la3d_fit_boxes_all:  byte masks in; two launches (scan with the preparation riding in it, dense fit);
+ *                        workspace as for la3d_fit_boxes
+ * ------------------------------------------------------------------------- */
+int la3d_fit_all_points(const float* depth, const void* prep, const uint32_t* bits, int B, int I, int H, int W,
+                        void* records, int rec_f64, la3d_stream_t stream);
+int la3d_fit_boxes_all(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
+                       int H, int W, int mask_is_01, void* workspace, size_t workspace_bytes, void* records, int rec_f64,
+                       la3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Multi-GPU form (images sharded across the GPUs of one NVLink / NVSwitch node, the reference's
  * --start_index/--end_index/--gpu_idx split of src/batch_scripts/whole.py:25-27,42): the fit kernel
  * writes every record straight into the gathered record buffer of EVERY rank through peer memory

@@ -41,6 +41,8 @@ SIGNATURES = {
     "la3d_fit_bits_workspace_bytes": (_sz, [_i, _i]),
     "la3d_fit_boxes_bits": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _i, _vp]),
     "la3d_fit_boxes_rle": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _vp, _i, _vp]),
+    "la3d_fit_all_points": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "la3d_fit_boxes_all": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp, _i, _vp]),
     "la3d_project_points": (_i, [_vp, _vp, _vp, C.c_longlong, _vp, _vp]),
 }
 

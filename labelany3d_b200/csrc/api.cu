@@ -209,6 +209,27 @@ extern "C" int la3d_fit_boxes_rle(const float* depth, const uint32_t* run_counts
   return fit_scanned_multi(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, &rec, 1, rec_f64, s, false);
 }
 
+// ---- every masked pixel instead of the 500-point subsample: two launches (scan with the preparation CTAs, dense fit)
+extern "C" int la3d_fit_boxes_all(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
+                                  int I, int H, int W, int mask_is_01, void* workspace, size_t workspace_bytes,
+                                  void* records, int rec_f64, la3d_stream_t stream) {
+  using namespace la3d;
+  LA3D_REQUIRE(depth && masks && K && workspace && records, "null pointer");
+  LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
+  LA3D_REQUIRE(I <= 8192, "at most 8192 instances per image");
+  LA3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+  const Workspace w = carve(workspace, B, I, H, W);
+  if (workspace_bytes < w.bytes) {
+    set_error("la3d_fit_boxes_all: workspace of %zu bytes, %zu needed", workspace_bytes, w.bytes);
+    return LA3D_ENOMEM;
+  }
+  const PrepView pv = prep_view(w.prep, B, I, prep_blocks(I));
+  const PrepArgs pa{K, ground, B, I, 0u, pv};              // cameras and ground rotations; the random words go unused
+  int rc = launch_mask_scan(masks, B * I, H, W, mask_is_01, w.bits, w.chunk_counts, &pa, static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  return la3d_fit_all_points(depth, w.prep, w.bits, B, I, H, W, records, rec_f64, stream);
+}
+
 extern "C" int la3d_fit_boxes_p2p(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
                                   int I, int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
                                   uint32_t image_offset, void* workspace, size_t workspace_bytes,

@@ -1,0 +1,302 @@
+// Oriented 3D box per instance from ALL masked pixels (no 500-point subsample) on sm_100a.
+//
+// The reference draws 500 of a mask's points at random before fitting (src/util_3dbox.py:123-125, an
+// unseeded global-RNG draw).  This kernel is estimate_bbox (src/util_3dbox.py:106-178, method='pca') with
+// that draw replaced by the identity: every set pixel of the plane takes part, so the result is
+// deterministic and uses all the data.  It is the "reduction" form of the path: per instance the
+// centroid / covariance sums and the extents are block-wide reductions over the masked pixels.
+//
+// One CTA of 256 threads per box, two sweeps over the plane's bit words (la3d_mask_scan /
+// la3d_rle_decode layout); zero words are skipped, set bits are walked with ffs:
+//   sweep 1: pixel -> depth -> exact float64 lift (src/util.py:72 operation order) -> p @ Rg -> NaN-row
+//            filter -> n, sum x, sum z, sum xx, sum xz, sum zz, min / max y;  then the closed-form first
+//            principal axis of scikit-learn's PCA(2) gives the yaw;
+//   sweep 2: the same points rotated by that yaw -> min / max x, z;
+//   tail:    float16-rounded corners, back-rotation with the reference's Rg / Rg^T convention, centre,
+//            dimensions, R_cam, projected corners and their 2D bounds - the same arithmetic as the tail of
+//            fit.cu's kernel.
+// Every thread adds its points in a fixed order and the partial sums are combined in a fixed tree, so the
+// record does not change from run to run.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace la3d {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct AllArgs {
+  const float* depth;
+  const uint32_t* bits;
+  const PrepCamera* cams;   // [images] intrinsics and their inverse (la3d_fit_prepare)
+  const double* Rg_pre;     // [boxes][9] ground rotations (la3d_fit_prepare)
+  int I, HW, W, words;      // words: bit words per plane (la3d_words_per_plane)
+  void* records;
+  int rec_f64;
+};
+
+__device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }   // NaN in b is ignored
+__device__ __forceinline__ double dmax(double a, double b) { return b > a ? b : a; }
+
+__device__ __forceinline__ void put(const AllArgs& a, size_t idx, double val) {
+  if (a.rec_f64) reinterpret_cast<double*>(a.records)[idx] = val;
+  else reinterpret_cast<float*>(a.records)[idx] = (float)val;
+}
+
+struct Smem {
+  double red[kWarps][8];
+  int ired[kWarps][4];
+  double Kinv[9], Kmat[9], Rg[9];
+  double yaw, cos_yaw, sin_yaw;
+  double rec[LA3D_REC];
+};
+
+// kind[k]: 0 sum, 1 min, 2 max.  Fixed combination order: xor tree inside a warp, then warps 0..7.
+template <int N>
+__device__ __forceinline__ void block_reduce(double (&v)[N], const int (&kind)[N], Smem& sm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_xor_sync(kFull, v[k], o);
+      v[k] = kind[k] == 0 ? v[k] + other : kind[k] == 1 ? dmin(v[k], other) : dmax(v[k], other);
+    }
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < N; ++k) sm.red[warp][k] = v[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double acc = sm.red[0][k];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) {
+      const double other = sm.red[w][k];
+      acc = kind[k] == 0 ? acc + other : kind[k] == 1 ? dmin(acc, other) : dmax(acc, other);
+    }
+    v[k] = acc;
+  }
+}
+
+__device__ __forceinline__ void block_sum_int(int (&v)[4], Smem& sm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = __reduce_add_sync(kFull, v[k]);
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sm.ired[warp][k] = v[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int acc = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) acc += sm.ired[w][k];
+    v[k] = acc;
+  }
+}
+
+// Calls f(rx, ry, rz) for every set pixel of the plane that this thread owns (words tid, tid+256, ...),
+// in ascending pixel order: the ground-aligned point p @ Rg of the pixel's lifted depth.
+template <typename F>
+__device__ __forceinline__ void for_each_point(const AllArgs& a, const uint32_t* __restrict__ plane,
+                                               const float* __restrict__ depth_img, const Smem& sm, F&& f) {
+  const int used = (a.HW + 31) >> 5;
+  for (int w = threadIdx.x; w < used; w += kThreads) {
+    uint32_t word = __ldg(plane + w);
+    if (!word) continue;
+    const int p0 = w << 5;
+    const int v0 = p0 / a.W, u0 = p0 - v0 * a.W;
+    while (word) {
+      const int k = __ffs((int)word) - 1;
+      word &= word - 1u;
+      const int p = p0 + k;
+      if (p >= a.HW) break;                       // padding bits of the last word (always zero)
+      int u = u0 + k, v = v0;
+      while (u >= a.W) { u -= a.W; ++v; }         // a word may run over the end of a row
+      const double d = (double)__ldg(depth_img + p);
+      double X, Y, Z;
+      lift_pixel_exact(d, (double)u, (double)v, sm.Kinv, X, Y, Z);
+      // np.dot(in_pc, Rg): r_j = sum_i p_i Rg[i][j]  (inf * 0 -> NaN drops the row, as in NumPy)
+      const double rx = X * sm.Rg[0] + Y * sm.Rg[3] + Z * sm.Rg[6];
+      const double ry = X * sm.Rg[1] + Y * sm.Rg[4] + Z * sm.Rg[7];
+      const double rz = X * sm.Rg[2] + Y * sm.Rg[5] + Z * sm.Rg[8];
+      f(rx, ry, rz);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) fit_all_kernel(AllArgs a) {
+  __shared__ Smem sm;
+  const int box = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int img = box / a.I;
+  if (tid < 9) sm.Kmat[tid] = __ldg(&a.cams[img].K[tid]);
+  else if (tid < 18) sm.Kinv[tid - 9] = __ldg(&a.cams[img].Kinv[tid - 9]);
+  else if (tid < 27) sm.Rg[tid - 18] = __ldg(a.Rg_pre + (size_t)box * 9 + (tid - 18));
+  __syncthreads();
+  const uint32_t* plane = a.bits + (size_t)box * a.words;
+  const float* depth_img = a.depth + (size_t)img * a.HW;
+
+  // ---- sweep 1: counts, NaN-row filter (util_3dbox.py:139-143), moments of the XZ footprint, y range ----
+  double s[7] = {0.0, 0.0, 0.0, 0.0, 0.0, CUDART_INF, -CUDART_INF};      // sums x, z, xx, xz, zz; min y; max y
+  int cnt[4] = {0, 0, 0, 0};                                             // valid, set pixels, inf in x/z, inf in y
+  for_each_point(a, plane, depth_img, sm, [&](double rx, double ry, double rz) {
+    ++cnt[1];
+    if (isnan(rx) || isnan(ry) || isnan(rz)) return;
+    ++cnt[0];
+    cnt[2] |= (int)(isinf(rx) || isinf(rz));
+    cnt[3] |= (int)isinf(ry);
+    s[0] += rx; s[1] += rz; s[2] += rx * rx; s[3] += rx * rz; s[4] += rz * rz;
+    s[5] = dmin(s[5], ry); s[6] = dmax(s[6], ry);
+  });
+  {
+    const int kind[7] = {0, 0, 0, 0, 0, 1, 2};
+    block_reduce(s, kind, sm);
+    block_sum_int(cnt, sm);
+  }
+  const int n_valid = cnt[0], n_src = cnt[1], inf_xz = cnt[2], inf_y = cnt[3];
+  int status = LA3D_ST_OK;
+  if (n_valid == 0) status = LA3D_ST_NO_VALID;
+  else if (inf_xz) status = LA3D_ST_NONFINITE;            // scikit-learn's input check raises
+  else if (n_valid == 1) status = LA3D_ST_PCA_UNDEFINED;  // PCA(2) needs 2 samples
+  if (status != LA3D_ST_OK) {                             // uniform across the CTA
+    for (int f = tid; f < LA3D_REC; f += kThreads) {
+      double val = CUDART_NAN;
+      if (f == LA3D_O_NVALID) val = (double)n_valid;
+      if (f == LA3D_O_STATUS) val = (double)status;
+      if (f == LA3D_O_NMASK) val = (double)n_src;
+      if (f == LA3D_O_PAD) val = 0.0;
+      put(a, (size_t)box * LA3D_REC + f, val);
+    }
+    return;
+  }
+
+  // ---- yaw: util_3dbox.py:181-186 with scikit-learn's arithmetic in closed form ----
+  if (tid == 0) {
+    const double n = (double)n_valid;
+    const double mx = s[0] / n, mz = s[1] / n;
+    const double ca = (s[2] - n * mx * mx) / (n - 1.0);
+    const double cb = (s[3] - n * mx * mz) / (n - 1.0);
+    const double cc = (s[4] - n * mz * mz) / (n - 1.0);
+    const double theta = 0.5 * atan2(2.0 * cb, ca - cc);
+    double vz, vx;
+    sincos(theta, &vz, &vx);
+    if (fabs(vx) >= fabs(vz)) { if (vx < 0.0) { vx = -vx; vz = -vz; } }
+    else if (vz < 0.0) { vx = -vx; vz = -vz; }
+    sm.cos_yaw = vx; sm.sin_yaw = vz;
+    sm.yaw = atan2(vz, vx);
+  }
+  __syncthreads();
+  const double yaw = sm.yaw, cy_ = sm.cos_yaw, sy_ = sm.sin_yaw;
+
+  // ---- sweep 2: extents at that yaw: rotate_y(yaw) @ pc^T, per-axis min / max (:154-160) ----
+  double e[4] = {CUDART_INF, CUDART_INF, -CUDART_INF, -CUDART_INF};      // min x, min z, max x, max z
+  for_each_point(a, plane, depth_img, sm, [&](double px, double py, double pz) {
+    if (isnan(px) || isnan(py) || isnan(pz)) return;
+    const double rx = cy_ * px + sy_ * pz, rz = cy_ * pz - sy_ * px;
+    e[0] = dmin(e[0], rx); e[2] = dmax(e[2], rx);
+    e[1] = dmin(e[1], rz); e[3] = dmax(e[3], rz);
+  });
+  {
+    const int kind[4] = {1, 1, 2, 2};
+    block_reduce(e, kind, sm);
+  }
+  double ext[6] = {e[0], s[5], e[1], e[2], s[6], e[3]};
+  if (inf_y) { ext[0] = ext[3] = ext[2] = ext[5] = CUDART_NAN; }        // 0 * inf in the x / z rows of the product
+  const double dim[3] = {ext[3] - ext[0], ext[4] - ext[1], ext[5] - ext[2]};
+  const double ctr[3] = {(ext[0] + ext[3]) / 2, (ext[1] + ext[4]) / 2, (ext[2] + ext[5]) / 2};
+
+  // ---- tail (the arithmetic of fit.cu's kernel, util_3dbox.py:165-176, util.py:227-229) ----
+  double* rec = sm.rec;
+  // rotate_y(-yaw) = [[c,0,-s],[0,1,0],[s,0,c]] with c = cos(yaw), s = sin(yaw)
+  const double Ry[9] = {cy_, 0.0, -sy_, 0.0, 1.0, 0.0, sy_, 0.0, cy_};
+  if (tid < 8) {
+    // convert_box_vertices(cx,cy,cz,dx,dy,dz,0).astype(float16)  (:71-103, :165)
+    const double sgx = (tid == 1 || tid == 2 || tid == 5 || tid == 6) ? 1.0 : -1.0;
+    const double sgy = (tid == 2 || tid == 3 || tid == 6 || tid == 7) ? 1.0 : -1.0;
+    const double sgz = (tid >= 4) ? 1.0 : -1.0;
+    const double lx = sgx * (dim[0] / 2), ly = sgy * (dim[1] / 2), lz = sgz * (dim[2] / 2);
+    double V[3];
+    V[0] = (lx * 1.0 + ly * 0.0 + lz * 0.0) + ctr[0];
+    V[1] = (lx * 0.0 + ly * 1.0 + lz * 0.0) + ctr[1];
+    V[2] = (lx * -0.0 + ly * 0.0 + lz * 1.0) + ctr[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) V[i] = (double)__half2float(__double2half(V[i]));
+    // vertices = (rotate_y(-yaw) @ V^T)^T @ Rg^T  (:168-169)
+    double v1[3], v2[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v1[i] = Ry[i * 3] * V[0] + Ry[i * 3 + 1] * V[1] + Ry[i * 3 + 2] * V[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v2[i] = v1[0] * sm.Rg[i * 3] + v1[1] * sm.Rg[i * 3 + 1] + v1[2] * sm.Rg[i * 3 + 2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rec[LA3D_O_VERT + tid * 3 + i] = v2[i];
+    // project_to_2d (util.py:227-229)
+    const double h0 = sm.Kmat[0] * v2[0] + sm.Kmat[1] * v2[1] + sm.Kmat[2] * v2[2];
+    const double h1 = sm.Kmat[3] * v2[0] + sm.Kmat[4] * v2[1] + sm.Kmat[5] * v2[2];
+    const double h2 = sm.Kmat[6] * v2[0] + sm.Kmat[7] * v2[1] + sm.Kmat[8] * v2[2];
+    rec[LA3D_O_UV + tid * 2] = h0 / h2;
+    rec[LA3D_O_UV + tid * 2 + 1] = h1 / h2;
+  } else if (tid == 32) {
+    // center_cam = Rg^T @ (rotate_y(-yaw) @ c)  (:172-173; Rg^T where the corners used Rg - kept)
+    double w[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w[i] = Ry[i * 3] * ctr[0] + Ry[i * 3 + 1] * ctr[1] + Ry[i * 3 + 2] * ctr[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rec[LA3D_O_CENTER + i] = sm.Rg[i] * w[0] + sm.Rg[3 + i] * w[1] + sm.Rg[6 + i] * w[2];
+    rec[LA3D_O_DIM] = dim[2]; rec[LA3D_O_DIM + 1] = dim[1]; rec[LA3D_O_DIM + 2] = dim[0];
+    rec[LA3D_O_YAW] = yaw;
+    rec[LA3D_O_NVALID] = (double)n_valid;
+    rec[LA3D_O_STATUS] = (double)LA3D_ST_OK;
+    rec[LA3D_O_NMASK] = (double)n_src;
+    rec[LA3D_O_PAD] = 0.0;
+  } else if (tid == 40) {
+    // R_cam = Rg^T @ rotate_y(-yaw)  (:176)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        rec[LA3D_O_RCAM + i * 3 + k] = sm.Rg[i] * Ry[k] + sm.Rg[3 + i] * Ry[3 + k] + sm.Rg[6 + i] * Ry[6 + k];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // Python min()/max() over the 8 projections (combine_results.py:241-246): sequential
+    // `if x < m` / `if x > m`, so a leading NaN sticks and a later NaN is skipped.
+    double mnu = rec[LA3D_O_UV], mnv = rec[LA3D_O_UV + 1], mxu = mnu, mxv = mnv;
+    for (int j = 1; j < 8; ++j) {
+      const double uu = rec[LA3D_O_UV + 2 * j], vv = rec[LA3D_O_UV + 2 * j + 1];
+      if (uu < mnu) mnu = uu;
+      if (vv < mnv) mnv = vv;
+      if (uu > mxu) mxu = uu;
+      if (vv > mxv) mxv = vv;
+    }
+    rec[LA3D_O_BOX2D] = mnu; rec[LA3D_O_BOX2D + 1] = mnv;
+    rec[LA3D_O_BOX2D + 2] = mxu; rec[LA3D_O_BOX2D + 3] = mxv;
+  }
+  __syncthreads();
+  for (int f = tid; f < LA3D_REC; f += kThreads) put(a, (size_t)box * LA3D_REC + f, rec[f]);
+}
+
+}  // namespace
+}  // namespace la3d
+
+extern "C" int la3d_fit_all_points(const float* depth, const void* prep, const uint32_t* bits, int B, int I, int H, int W,
+                                   void* records, int rec_f64, la3d_stream_t stream) {
+  using namespace la3d;
+  LA3D_REQUIRE(depth && prep && bits && records, "null pointer");
+  LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
+  LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
+  LA3D_REQUIRE(I <= 8192, "at most 8192 instances per image");
+  const PrepView pv = prep_view(const_cast<void*>(prep), B, I, prep_blocks(I));
+  AllArgs a{};
+  a.depth = depth; a.bits = bits; a.cams = pv.cams; a.Rg_pre = pv.Rg;
+  a.I = I; a.HW = H * W; a.W = W; a.words = (int)la3d_words_per_plane(H, W);
+  a.records = records; a.rec_f64 = rec_f64;
+  fit_all_kernel<<<(unsigned)(B * I), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  LA3D_CUDA(cudaGetLastError());
+  return LA3D_OK;
+}

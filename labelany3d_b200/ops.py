@@ -476,6 +476,54 @@ def fit_boxes_bits(depth, K, bits, chunk_counts, I, ground=None, method="pca", y
     return rec
 
 
+def fit_boxes_all(depth, K, masks, ground=None, out_dtype=torch.float64):
+    """Boxes from EVERY masked pixel (``la3d_fit_boxes_all``): the reference's ``estimate_bbox`` with
+    ``method='pca'`` and its random 500-point draw (``src/util_3dbox.py:123-125``) replaced by the identity.
+    Deterministic, no generator involved; same record layout and status codes as :func:`fit_boxes`.
+    Two launches: the mask scan (with the camera / ground preparation riding in its grid) and one CTA per box
+    that reduces the footprint's moments and extents over all its pixels."""
+    lib = _lib.load()
+    depth = _need_cuda("depth", depth, torch.float32)
+    K = _need_cuda("K", K, torch.float64)
+    masks = _need_cuda("masks", masks)
+    B, I, H, W = masks.shape
+    if tuple(depth.shape) != (B, H, W) or tuple(K.shape) != (B, 3, 3):
+        raise ValueError("depth / K do not match the mask stack")
+    if ground is not None:
+        ground = _need_cuda("ground", ground, torch.float64)
+        if tuple(ground.shape) != (B, I, 3):
+            raise ValueError(f"ground must be [{B},{I},3]")
+    if out_dtype not in (torch.float32, torch.float64):
+        raise TypeError("out_dtype must be float32 or float64")
+    m8, is01 = _masks_u8(masks)
+    dev = depth.device
+    ws_bytes = int(lib.la3d_fit_workspace_bytes(B, I, H, W))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rec = torch.empty((B, I, REC), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.la3d_fit_boxes_all(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01, _ptr(ws), ws_bytes,
+                                    _ptr(rec), int(out_dtype == torch.float64), _stream())
+    _lib.check(rc, "la3d_fit_boxes_all")
+    return rec
+
+
+def fit_all_points(depth, prep, bits, I, out_dtype=torch.float64):
+    """The dense fit alone (``la3d_fit_all_points``) on bit planes that already exist
+    (:func:`mask_scan` / :func:`rle_decode`) and the ``prep`` buffer of :func:`fit_prepare`."""
+    lib = _lib.load()
+    depth = _need_cuda("depth", depth, torch.float32)
+    bits = _need_cuda("bits", bits, torch.int32)
+    B, H, W = depth.shape
+    if tuple(bits.shape) != (B * I, scan_layout(H, W)[1]):
+        raise ValueError("bit planes do not match depth and I")
+    rec = torch.empty((B, I, REC), dtype=out_dtype, device=depth.device)
+    with torch.cuda.device(depth.device):
+        rc = lib.la3d_fit_all_points(_ptr(depth), _ptr(prep), _ptr(bits), B, I, H, W, _ptr(rec),
+                                     int(out_dtype == torch.float64), _stream())
+    _lib.check(rc, "la3d_fit_all_points")
+    return rec
+
+
 class RleBoxFitter:
     """``BoxFitter`` for masks given as COCO run-length annotations (``la3d_fit_boxes_rle``): one call =
     three launches (decode with the preparation riding in its grid, subsample ranks, fit); the byte masks

@@ -533,12 +533,14 @@ def fit_points_record(pc, K, ground=None, method="pca", yaw_steps=None, rng=None
 
 
 def fit_boxes(depth, K, masks, ground=None, method="pca", yaw_steps=None, seed=0, image_offset=0,
-              impl="library"):
+              impl="library", subsample=True):
     """``depth[B,H,W] f32, K[B,3,3], masks[B,I,H,W], ground[B,I,3]|None`` -> ``[B,I,64]`` f64.
 
     Per image ``b`` the legacy RandomState is re-seeded with
     ``seed + image_offset + b`` and instances draw from it in order, exactly as
     the reference would if ``np.random.seed`` were called before each image.
+    ``subsample=False``: the random 500-point draw of ``src/util_3dbox.py:123-125`` is replaced by
+    the identity (every masked point takes part; what ``la3d_fit_all_points`` computes).
     """
     depth = np.asarray(depth)
     masks = np.asarray(masks)
@@ -551,5 +553,6 @@ def fit_boxes(depth, K, masks, ground=None, method="pca", yaw_steps=None, seed=0
         for i in range(I):
             pc = masked_points(pts, masks[b, i])
             g = None if ground is None else ground[b, i]
-            out[b, i] = fit_points_record(pc, K[b], g, method, yaw_steps, rng=rng, impl=impl)
+            every = None if subsample or pc.shape[0] <= SUBSAMPLE else np.arange(pc.shape[0])
+            out[b, i] = fit_points_record(pc, K[b], g, method, yaw_steps, rng=rng, impl=impl, sample_idx=every)
     return out

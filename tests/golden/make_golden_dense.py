@@ -1,0 +1,85 @@
+"""Golden vectors for the all-pixels fit (``la3d_fit_all_points``), minted from the UNMODIFIED reference.
+Run in the build container:
+
+    python tests/golden/make_golden_dense.py
+
+The all-pixels mode is the reference's ``estimate_bbox`` (``src/util_3dbox.py:106-178``, ``method='pca'``) with
+its random 500-point draw (``:123-125``) replaced by the identity.  That is exactly what this script makes the
+unmodified reference function compute: while it runs, ``numpy.random.randint`` (the one name the draw goes
+through) returns ``arange(high)``, so ``in_pc[rand_ind]`` is ``in_pc``.  Inputs: the composed scene of
+``golden_v1.npz`` (3 images 96x128, 4 instances: empty mask, one pixel, 200 pixels, inf / NaN depths), plus
+two larger scenes so that masks of several thousand pixels are covered; with and without ground normals.
+Output: ``tests/golden/golden_dense_v1.npz``; the oracle (``fit_boxes(..., subsample=False)``) is asserted
+against it here (``impl="library"``: bit-identical; ``impl="closed"``: 1e-9 x scale).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import dense_cases  # noqa: E402
+import live_reference  # noqa: E402
+from oracle import la3d_oracle as orc  # noqa: E402
+
+
+def reference_records(util, box, comb, depth, K, masks, ground):
+    B, I = masks.shape[:2]
+    rec = np.full((B, I, orc.REC), np.nan)
+    real_randint = np.random.randint
+    np.random.randint = lambda low, high=None, size=None: np.arange(high)        # the identity draw
+    try:
+        for b in range(B):
+            with np.errstate(invalid="ignore"):
+                pts3 = util.depth_to_points(depth[b][None], K[b])
+            for i in range(I):
+                pc = pts3[masks[b, i]]
+                g = None if ground is None else ground[b, i]
+                try:
+                    with live_reference.quiet(), np.errstate(invalid="ignore", over="ignore"):
+                        v, ctr, dim, Rc = box.estimate_bbox(pc, None, g, "pca")
+                except ValueError as exc:
+                    rec[b, i] = orc.failed_record(orc.status_of_exception(exc), np.nan, pc.shape[0])
+                    continue
+                uv = np.stack([comb.project_to_2d(np.array(p), K[b]) for p in v])
+                proj = [uv[:, 0].min(), uv[:, 1].min(), uv[:, 0].max(), uv[:, 1].max()]
+                rec[b, i] = orc.pack_record(v, ctr, dim, Rc, np.nan, np.nan, orc.ST_OK, uv, proj, pc.shape[0])
+    finally:
+        np.random.randint = real_randint
+    return rec
+
+
+def main():
+    util, box, comb = live_reference.load()
+    G = {}
+    sel = np.ones(orc.REC, dtype=bool)
+    sel[[orc.O_YAW, orc.O_NVALID]] = False        # not observable through the reference API
+    worst = {}
+    for name, (depth, K, masks, ground) in dense_cases.scenes().items():
+        for use_ground in (0, 1):
+            g = ground if use_ground else None
+            rec = reference_records(util, box, comb, depth, K, masks, g)
+            G[f"{name}/g{use_ground}/records"] = rec
+            for impl in ("library", "closed"):
+                mine = orc.fit_boxes(depth, K, masks, g, "pca", impl=impl, subsample=False)
+                a, b = mine[..., sel], rec[..., sel]
+                same = np.isnan(a) & np.isnan(b)
+                scale = np.maximum(1.0, np.nanmax(np.abs(np.where(np.isfinite(b), b, 0.0)), axis=-1, keepdims=True))
+                d = np.where(same, 0.0, np.abs(a - b) / scale)
+                worst[impl] = max(worst.get(impl, 0.0), float(np.nanmax(d)))
+                assert not np.isnan(d).any(), (name, use_ground, impl)
+            print(name, use_ground, "pixels per mask", rec[..., orc.O_NMASK].astype(int).tolist(), "status",
+                  rec[..., orc.O_STATUS].astype(int).tolist())
+    assert worst["library"] == 0.0, worst
+    assert worst["closed"] < 1e-9, worst
+    out = os.path.join(HERE, "golden_dense_v1.npz")
+    np.savez_compressed(out, **G)
+    print(f"wrote {out}: {len(G)} arrays; oracle vs reference (relative to the record's scale): {worst}")
+
+
+if __name__ == "__main__":
+    main()
