@@ -19,6 +19,8 @@
 // record does not change from run to run.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace la3d {
@@ -130,6 +132,41 @@ __device__ __forceinline__ void for_each_point(const AllArgs& a, const uint32_t*
   }
 }
 
+// The same walk, warp-cooperatively: a warp takes 32 consecutive words, and every non-empty one of them (found with
+// a ballot) is handled by the whole warp, lane k taking bit k - so the lanes are busy on the dense words inside
+// a mask instead of idling while the few lanes that own those words walk 32 bits each.
+template <typename F>
+__device__ __forceinline__ void for_each_point_coop(const AllArgs& a, const uint32_t* __restrict__ plane,
+                                                    const float* __restrict__ depth_img, const Smem& sm, F&& f) {
+  const int used = (a.HW + 31) >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int wbase = warp * 32; wbase < used; wbase += kThreads) {        // warp-uniform trip count
+    const int w = wbase + lane;
+    const uint32_t mine = (w < used) ? __ldg(plane + w) : 0u;
+    unsigned nonempty = __ballot_sync(kFull, mine != 0u);
+    while (nonempty) {                                                   // warp-uniform
+      const int src = __ffs((int)nonempty) - 1;
+      nonempty &= nonempty - 1u;
+      const uint32_t word = __shfl_sync(kFull, mine, src);
+      if (!((word >> lane) & 1u)) continue;
+      const int p0 = (wbase + src) << 5;
+      const int p = p0 + lane;
+      if (p >= a.HW) continue;                                           // padding bits of the last word (always zero)
+      int v = p0 / a.W;
+      int u = p0 - v * a.W + lane;
+      while (u >= a.W) { u -= a.W; ++v; }                                // a word may run over the end of a row
+      const double d = (double)__ldg(depth_img + p);
+      double X, Y, Z;
+      lift_pixel_exact(d, (double)u, (double)v, sm.Kinv, X, Y, Z);
+      const double rx = X * sm.Rg[0] + Y * sm.Rg[3] + Z * sm.Rg[6];
+      const double ry = X * sm.Rg[1] + Y * sm.Rg[4] + Z * sm.Rg[7];
+      const double rz = X * sm.Rg[2] + Y * sm.Rg[5] + Z * sm.Rg[8];
+      f(rx, ry, rz);
+    }
+  }
+}
+
+template <bool kCoop>
 __global__ void __launch_bounds__(kThreads) fit_all_kernel(AllArgs a) {
   __shared__ Smem sm;
   const int box = blockIdx.x;
@@ -145,7 +182,11 @@ __global__ void __launch_bounds__(kThreads) fit_all_kernel(AllArgs a) {
   // ---- sweep 1: counts, NaN-row filter (util_3dbox.py:139-143), moments of the XZ footprint, y range ----
   double s[7] = {0.0, 0.0, 0.0, 0.0, 0.0, CUDART_INF, -CUDART_INF};      // sums x, z, xx, xz, zz; min y; max y
   int cnt[4] = {0, 0, 0, 0};                                             // valid, set pixels, inf in x/z, inf in y
-  for_each_point(a, plane, depth_img, sm, [&](double rx, double ry, double rz) {
+  auto sweep = [&](auto&& f) {
+    if (kCoop) for_each_point_coop(a, plane, depth_img, sm, f);
+    else for_each_point(a, plane, depth_img, sm, f);
+  };
+  sweep([&](double rx, double ry, double rz) {
     ++cnt[1];
     if (isnan(rx) || isnan(ry) || isnan(rz)) return;
     ++cnt[0];
@@ -196,7 +237,7 @@ __global__ void __launch_bounds__(kThreads) fit_all_kernel(AllArgs a) {
 
   // ---- sweep 2: extents at that yaw: rotate_y(yaw) @ pc^T, per-axis min / max (:154-160) ----
   double e[4] = {CUDART_INF, CUDART_INF, -CUDART_INF, -CUDART_INF};      // min x, min z, max x, max z
-  for_each_point(a, plane, depth_img, sm, [&](double px, double py, double pz) {
+  sweep([&](double px, double py, double pz) {
     if (isnan(px) || isnan(py) || isnan(pz)) return;
     const double rx = cy_ * px + sy_ * pz, rz = cy_ * pz - sy_ * px;
     e[0] = dmin(e[0], rx); e[2] = dmax(e[2], rx);
@@ -296,7 +337,10 @@ extern "C" int la3d_fit_all_points(const float* depth, const void* prep, const u
   a.depth = depth; a.bits = bits; a.cams = pv.cams; a.Rg_pre = pv.Rg;
   a.I = I; a.HW = H * W; a.W = W; a.words = (int)la3d_words_per_plane(H, W);
   a.records = records; a.rec_f64 = rec_f64;
-  fit_all_kernel<<<(unsigned)(B * I), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  // LA3D_FITALL_VARIANT=1: warp-cooperative walk of the set bits (lane = bit) instead of one thread per word
+  const char* env = getenv("LA3D_FITALL_VARIANT");
+  if (env && atoi(env) == 1) fit_all_kernel<true><<<(unsigned)(B * I), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  else fit_all_kernel<false><<<(unsigned)(B * I), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
 }
