@@ -7,7 +7,8 @@
 // centroid / covariance sums and the extents are block-wide reductions over the masked pixels.
 //
 // One CTA of 256 threads per box, two sweeps over the plane's bit words (la3d_mask_scan /
-// la3d_rle_decode layout); zero words are skipped, set bits are walked with ffs:
+// la3d_rle_decode layout); a warp takes 32 consecutive words and every non-empty one of them is handled by
+// the whole warp, lane k taking bit k:
 //   sweep 1: pixel -> depth -> exact float64 lift (src/util.py:72 operation order) -> p @ Rg -> NaN-row
 //            filter -> n, sum x, sum z, sum xx, sum xz, sum zz, min / max y;  then the closed-form first
 //            principal axis of scikit-learn's PCA(2) gives the yaw;
@@ -16,7 +17,7 @@
 //            dimensions, R_cam, projected corners and their 2D bounds - the same arithmetic as the tail of
 //            fit.cu's kernel.
 // Every thread adds its points in a fixed order and the partial sums are combined in a fixed tree, so the
-// record does not change from run to run.
+// record does not change from run to run (the two walk orders differ in the last bits of the sums only).
 #include <math_constants.h>
 
 #include <cstdlib>
@@ -337,9 +338,10 @@ extern "C" int la3d_fit_all_points(const float* depth, const void* prep, const u
   a.depth = depth; a.bits = bits; a.cams = pv.cams; a.Rg_pre = pv.Rg;
   a.I = I; a.HW = H * W; a.W = W; a.words = (int)la3d_words_per_plane(H, W);
   a.records = records; a.rec_f64 = rec_f64;
-  // LA3D_FITALL_VARIANT=1: warp-cooperative walk of the set bits (lane = bit) instead of one thread per word
+  // default: warp-cooperative walk of the set bits (lane = bit); LA3D_FITALL_VARIANT=0 selects the first form, one
+  // thread per word (measured on B200, config 2: 0.86 ms vs 2.04 ms per step)
   const char* env = getenv("LA3D_FITALL_VARIANT");
-  if (env && atoi(env) == 1) fit_all_kernel<true><<<(unsigned)(B * I), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  if (!env || atoi(env) != 0) fit_all_kernel<true><<<(unsigned)(B * I), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   else fit_all_kernel<false><<<(unsigned)(B * I), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
