@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LA3D_VERSION 100 /* 0.1.0 */
+#define LA3D_VERSION 200 /* 0.2.0 */
 
 typedef void* la3d_stream_t; /* cudaStream_t */
 
@@ -241,29 +241,64 @@ int la3d_fit_boxes_all(const float* depth, const uint8_t* masks, const double* K
                        la3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
- * Multi-GPU form (images sharded across the GPUs of one NVLink / NVSwitch node, the reference's
- * --start_index/--end_index/--gpu_idx split of src/batch_scripts/whole.py:25-27,42): the fit kernel
- * writes every record straight into the gathered record buffer of EVERY rank through peer memory
- * (peer_records[p] = rank p's gathered buffer + this rank's slot; include the local one), so the
- * all-gather costs no extra pass; la3d_peer_barrier then tells each rank that all slots have landed.
- *   peer_records: HOST array of n_peers (<= LA3D_MAX_PEERS) device pointers, peer-mapped
- *   flags:        HOST array of `world` device pointers; flags[p] = rank p's array of >= world uint32
- *                 (peer-mapped, zero-initialised once); epoch must grow by one per barrier
- *   status:       nullable device int, set to 1 if a peer did not arrive within ~2 s
- *   wait_before_fit: nullable cudaEvent_t; `stream` waits for it between the sampler and the fit
- *                 kernel.  Pass the event recorded after the PREVIOUS step's la3d_peer_barrier (run on
- *                 another stream): the peer buffers are then known to be free again exactly when the
- *                 fit starts writing them, and the barrier hides under this step's scan and sampler.
+ * Record sinks: where the records of a fit go.  Every fit entry point above has a `_to` form that takes a
+ * la3d_sink instead of (records, rec_f64):
+ *   - n_out = 1, flags[0] = NULL: one local buffer (what the plain forms do);
+ *   - the multi-GPU form (images sharded across the GPUs of one NVLink / NVSwitch node, the reference's
+ *     --start_index/--end_index/--gpu_idx split of src/batch_scripts/whole.py:25-27,42 followed by the merge of
+ *     the per-process results): records[p] = rank p's gathered record buffer + THIS rank's slot (include the
+ *     local one), peer-mapped; the box kernel stores every record straight into all n_out buffers over NVLink,
+ *     so the all-gather of the packed records costs no extra pass.  The cross-GPU
+ *     synchronisation is done by the same kernel:
+ *       flags[p]  rank p's flag row, >= n_out uint32, peer-mapped, zero-initialised once
+ *       counter   one uint32 of LOCAL device memory, zero-initialised once
+ *       status    nullable int32 in host-visible (pinned) or device memory, zero-initialised once
+ *       epoch     the step number: 1 for the first call, growing by one per call, the same on every rank
+ *       rank      this rank's index (its column in every flag row)
+ *     Before its first store a CTA waits until every slot of flags[rank] has reached epoch-1 (the peers are
+ *     past the step that last read the buffers about to be overwritten: alternate between TWO gathered
+ *     buffers per rank, and consume a gathered buffer on the stream that issues the next call); the last
+ *     CTA of the grid to finish stores `epoch` into slot `rank` of every rank's row (release, system scope).
+ *     A consumer of the gathered records first waits for la3d_peer_wait(flags, rank, n_out, epoch).
+ *     A rank without images in a step calls la3d_peer_signal instead of a fit.
+ *     A peer that does not arrive within the timeout (default 120 s, LA3D_PEER_TIMEOUT_MS or
+ *     la3d_set_peer_timeout_ms) is fatal: *status is set to 1 and the kernel traps, so the host sees a CUDA
+ *     error instead of stale records.
+ * All destination buffers must be 16-byte aligned (records are stored 16 bytes at a time).
  * ------------------------------------------------------------------------- */
 #define LA3D_MAX_PEERS 8
-int la3d_fit_boxes_p2p(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
-                       int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed, uint32_t image_offset,
-                       void* workspace, size_t workspace_bytes, void* const* peer_records, int n_peers, int rec_f64,
-                       void* wait_before_fit, la3d_stream_t stream);
-int la3d_fit_scanned_p2p(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
-                         const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
-                         void* const* peer_records, int n_peers, int rec_f64, la3d_stream_t stream);
-int la3d_peer_barrier(uint32_t* const* flags, int rank, int world, uint32_t epoch, int* status, la3d_stream_t stream);
+typedef struct la3d_sink {
+  void* records[LA3D_MAX_PEERS];
+  uint32_t* flags[LA3D_MAX_PEERS];
+  uint32_t* counter;
+  int32_t* status;
+  uint32_t epoch;
+  int32_t n_out;
+  int32_t rank;
+  int32_t rec_f64;
+} la3d_sink;
+
+int la3d_fit_scanned_to(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
+                        const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
+                        const la3d_sink* sink, la3d_stream_t stream);
+int la3d_fit_boxes_to(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
+                      int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed, uint32_t image_offset,
+                      void* workspace, size_t workspace_bytes, const la3d_sink* sink, la3d_stream_t stream);
+int la3d_fit_boxes_rle_to(const float* depth, const uint32_t* run_counts, const int64_t* run_offsets, int max_runs,
+                          uint32_t* ends_ws, const double* K, const double* ground, int B, int I, int H, int W,
+                          int method, int yaw_steps, uint32_t seed, uint32_t image_offset, void* workspace,
+                          size_t workspace_bytes, int32_t* rle_status, const la3d_sink* sink, la3d_stream_t stream);
+int la3d_fit_boxes_all_to(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
+                          int H, int W, int mask_is_01, int method, int yaw_steps, void* workspace,
+                          size_t workspace_bytes, const la3d_sink* sink, la3d_stream_t stream);
+
+/* Stand-alone flag operations on `stream` (one tiny launch each).  flags: HOST array of `world` device
+ * pointers (the flag rows); la3d_peer_wait only dereferences flags[rank]. */
+int la3d_peer_signal(uint32_t* const* flags, int rank, int world, uint32_t epoch, la3d_stream_t stream);
+int la3d_peer_wait(uint32_t* const* flags, int rank, int world, uint32_t epoch, int32_t* status, la3d_stream_t stream);
+int la3d_peer_barrier(uint32_t* const* flags, int rank, int world, uint32_t epoch, int32_t* status,
+                      la3d_stream_t stream);
+void la3d_set_peer_timeout_ms(long long ms);
 
 /* ---------------------------------------------------------------------------
  * Oriented box from explicit point sets.  Replaces estimate_bbox,

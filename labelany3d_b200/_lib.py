@@ -30,9 +30,14 @@ SIGNATURES = {
     "la3d_fit_scanned": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "la3d_fit_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "la3d_fit_boxes": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _i, _vp]),
-    "la3d_fit_boxes_p2p": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _i, _i, _vp, _vp]),
-    "la3d_fit_scanned_p2p": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "la3d_fit_boxes_to": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _vp]),
+    "la3d_fit_scanned_to": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "la3d_fit_boxes_rle_to": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _vp, _vp]),
+    "la3d_fit_boxes_all_to": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
+    "la3d_peer_signal": (_i, [_vp, _i, _i, _u32, _vp]),
+    "la3d_peer_wait": (_i, [_vp, _i, _i, _u32, _vp, _vp]),
     "la3d_peer_barrier": (_i, [_vp, _i, _i, _u32, _vp, _vp]),
+    "la3d_set_peer_timeout_ms": (None, [C.c_longlong]),
     "la3d_fit_points": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "la3d_iou_matrix": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "la3d_box2d_from_corners": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
@@ -45,6 +50,29 @@ SIGNATURES = {
     "la3d_fit_boxes_all": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp, _i, _vp]),
     "la3d_project_points": (_i, [_vp, _vp, _vp, C.c_longlong, _vp, _vp]),
 }
+
+MAX_PEERS = 8
+
+
+class Sink(C.Structure):
+    """``la3d_sink`` of include/la3d.h: the destinations of a fit's records and the peer synchronisation."""
+    _fields_ = [("records", _vp * MAX_PEERS), ("flags", _vp * MAX_PEERS), ("counter", _vp), ("status", _vp),
+                ("epoch", _u32), ("n_out", C.c_int32), ("rank", C.c_int32), ("rec_f64", C.c_int32)]
+
+
+def make_sink(records, rec_f64, flags=None, counter=None, status=None, epoch=0, rank=0):
+    """``records``: list of device pointers (ints); ``flags``: list of the ranks' flag-row pointers or None."""
+    s = Sink()
+    for p, ptr in enumerate(records):
+        s.records[p] = ptr
+    s.n_out = len(records)
+    s.rec_f64 = int(bool(rec_f64))
+    if flags is not None:
+        for p, ptr in enumerate(flags):
+            s.flags[p] = ptr
+        s.counter, s.status, s.epoch, s.rank = counter, status, int(epoch) & 0xFFFFFFFF, int(rank)
+    return s
+
 
 _lib = None
 

@@ -77,3 +77,34 @@ def pack_runs(run_lists):
     counts = (np.concatenate([np.asarray(r, dtype=np.uint32) for r in run_lists]) if len(run_lists) and offsets[-1]
               else np.zeros(0, dtype=np.uint32))
     return counts, offsets, int(sizes.max()) if len(run_lists) else 0
+
+
+def runs_from_masks_device(masks):
+    """:func:`runs_from_mask` + :func:`pack_runs` for a whole stack on its device with torch:
+    ``masks[P,H,W]`` (bool / uint8 tensor) -> ``(counts int32[total] tensor, offsets int64[P+1] tensor,
+    max_runs int)``.  Input preparation for benchmarks and tests (the annotations of a real run come from
+    COCO JSON); equal to the NumPy form, which a GPU test asserts."""
+    import torch
+    P, H, W = masks.shape
+    HW = H * W
+    flat = (masks != 0).transpose(1, 2).reshape(P, HW)              # column-major pixel order
+    first = flat[:, 0].to(torch.int64)                               # a plane that starts set gets a leading 0-run
+    change = flat[:, 1:] != flat[:, :-1]
+    c = change.sum(dim=1, dtype=torch.int64)
+    nruns = c + 1 + first
+    offsets = torch.zeros(P + 1, dtype=torch.int64, device=masks.device)
+    torch.cumsum(nruns, 0, out=offsets[1:])
+    total = int(offsets[-1].item())
+    ends = torch.empty(total, dtype=torch.int64, device=masks.device)
+    idx = change.nonzero()                                           # sorted by plane, then position
+    plane, pos = idx[:, 0], idx[:, 1] + 1
+    cstart = torch.cumsum(c, 0) - c                                  # exclusive prefix of the change counts
+    k = torch.arange(idx.shape[0], device=masks.device) - cstart[plane]
+    ends[offsets[:-1][plane] + first[plane] + k] = pos
+    ends[offsets[1:] - 1] = HW
+    lead = first.nonzero()[:, 0]
+    ends[offsets[:-1][lead]] = 0
+    prev = torch.cat([ends.new_zeros(1), ends[:-1]])
+    prev[offsets[:-1]] = 0
+    counts = (ends - prev).to(torch.int32)
+    return counts, offsets, int(nruns.max().item())

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include "prep.cuh"
+#include "sink.cuh"
 
 namespace la3d {
 namespace {
@@ -31,10 +32,6 @@ int cuda_fail(cudaError_t err, const char* what) {
   set_error("CUDA error %d (%s) at %s", (int)err, cudaGetErrorString(err), what);
   return LA3D_ECUDA;
 }
-
-struct PeerFlags {
-  uint32_t* flags[LA3D_MAX_PEERS];
-};
 
 struct Workspace {
   uint32_t* bits;
@@ -74,11 +71,61 @@ extern "C" size_t la3d_fit_workspace_bytes(int B, int I, int H, int W) {
 }
 
 namespace la3d {
-static int fit_boxes_multi(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
-                           int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
-                           uint32_t image_offset, void* workspace, size_t workspace_bytes, void* const* records,
-                           int n_out, int rec_f64, void* wait_before_fit, la3d_stream_t stream) {
-  LA3D_REQUIRE(depth && masks && K && workspace && records, "null pointer");
+// ---- record sinks (sink.cuh) ---------------------------------------------------------------
+// A peer that does not reach a flag within this time is fatal (sticky status word + trap).  Far above ordinary
+// rank skew (first-call lazy initialisation, data loading, host preemption); LA3D_PEER_TIMEOUT_MS or
+// la3d_set_peer_timeout_ms() change it.
+static long long g_peer_timeout_ms = -1;
+unsigned long long peer_timeout_ns() {
+  if (g_peer_timeout_ms < 0) {
+    const char* env = getenv("LA3D_PEER_TIMEOUT_MS");
+    g_peer_timeout_ms = (env && atoll(env) > 0) ? atoll(env) : 120000;
+  }
+  return (unsigned long long)g_peer_timeout_ms * 1000000ull;
+}
+
+RecordSink local_sink(void* records, int rec_f64) {
+  RecordSink s{};
+  s.out[0] = records;
+  s.n_out = 1;
+  s.rec_f64 = rec_f64;
+  return s;
+}
+
+int sink_from_public(const la3d_sink* pub, RecordSink* out) {
+  LA3D_REQUIRE(pub && out, "null pointer (sink)");
+  LA3D_REQUIRE(pub->n_out >= 1 && pub->n_out <= LA3D_MAX_PEERS, "between 1 and LA3D_MAX_PEERS destinations");
+  RecordSink s{};
+  for (int p = 0; p < pub->n_out; ++p) {
+    LA3D_REQUIRE(pub->records[p] != nullptr, "null destination buffer");
+    LA3D_REQUIRE((reinterpret_cast<uintptr_t>(pub->records[p]) & 15u) == 0, "destination buffers must be 16-byte aligned");
+    s.out[p] = pub->records[p];
+  }
+  s.n_out = pub->n_out;
+  s.rec_f64 = pub->rec_f64 ? 1 : 0;
+  if (pub->flags[0]) {
+    LA3D_REQUIRE(pub->counter != nullptr, "peer synchronisation needs the local counter word");
+    LA3D_REQUIRE(pub->rank >= 0 && pub->rank < pub->n_out, "rank outside the destinations");
+    LA3D_REQUIRE(pub->epoch != 0, "epochs start at 1");
+    for (int p = 0; p < pub->n_out; ++p) {
+      LA3D_REQUIRE(pub->flags[p] != nullptr, "null flag row");
+      s.flags[p] = pub->flags[p];
+    }
+    s.counter = pub->counter;
+    s.status = pub->status;
+    s.epoch = pub->epoch;
+    s.rank = pub->rank;
+    s.timeout_ns = peer_timeout_ns();
+  }
+  *out = s;
+  return LA3D_OK;
+}
+
+static int fit_boxes_sink(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
+                          int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
+                          uint32_t image_offset, void* workspace, size_t workspace_bytes, const RecordSink& sink,
+                          la3d_stream_t stream) {
+  LA3D_REQUIRE(depth && masks && K && workspace, "null pointer");
   LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
   const Workspace w = carve(workspace, B, I, H, W);
@@ -96,42 +143,61 @@ static int fit_boxes_multi(const float* depth, const uint8_t* masks, const doubl
   rc = launch_sample(w.chunk_counts, pv, B, I, (int)la3d_chunks_per_plane(H, W), w.counts, w.ranks,
                      static_cast<cudaStream_t>(stream), pdl_enabled());
   if (rc) return rc;
-  // multi-GPU: the records go into peer buffers that may still be read from the step before last;
-  // the caller's event (the peer barrier of the previous step) gates only the fit, so that barrier
-  // and the skew between ranks hide under this step's scan and sampler
-  if (wait_before_fit)
-    LA3D_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(wait_before_fit), 0));
-  return fit_scanned_multi(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, records, n_out,
-                           rec_f64, static_cast<cudaStream_t>(stream), pdl_enabled() && !wait_before_fit);
+  return fit_scanned_sink(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, sink,
+                          static_cast<cudaStream_t>(stream), pdl_enabled());
 }
 
-// Cross-GPU barrier over peer memory: rank r stores `epoch` into slot r of every peer's flag array
-// (release, system scope), then waits until every slot of its own array has reached `epoch`.
-// Epochs only grow, so the flags never need a reset.  status[0] is set to 1 if a peer does not show up
-// within ~2 s (the kernel returns instead of hanging the GPU).
-__global__ void peer_barrier_kernel(PeerFlags pf, int rank, int world, uint32_t epoch, int* status) {
+// Cross-GPU flag operations over peer memory (the fit kernels do both halves themselves, sink.cuh; these
+// are the stand-alone forms).  signal: rank r stores `epoch` into slot r of every rank's flag row (release,
+// system scope).  wait: until every slot of the own row has reached `epoch`.  Epochs only grow, so the flags
+// never need a reset.  A peer that does not arrive within the timeout is fatal (wait_flag).
+__global__ void peer_sync_kernel(RecordSink s, int do_signal, int do_wait) {
   const int p = threadIdx.x;
-  if (p >= world) return;
-  __threadfence_system();
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.flags[p] + rank), "r"(epoch) : "memory");
-  const uint32_t* mine = pf.flags[rank] + p;
-  const long long t0 = clock64();
-  for (;;) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-    if ((int32_t)(v - epoch) >= 0) break;
-    if (clock64() - t0 > 4000000000ll) { if (status) *status = 1; break; }
-    __nanosleep(64);
+  if (p >= s.n_out) return;
+  if (do_signal) {
+    __threadfence_system();
+    st_release_sys(s.flags[p] + s.rank, s.epoch);
   }
+  if (do_wait) wait_flag(s.flags[s.rank] + p, s.epoch, s.status, s.timeout_ns);
+}
+
+static int peer_sync(uint32_t* const* flags, int rank, int world, uint32_t epoch, int32_t* status, int do_signal,
+                     int do_wait, la3d_stream_t stream) {
+  LA3D_REQUIRE(flags, "null pointer");
+  LA3D_REQUIRE(world >= 1 && world <= LA3D_MAX_PEERS && rank >= 0 && rank < world, "bad rank / world");
+  RecordSink s{};
+  for (int p = 0; p < world; ++p) {
+    LA3D_REQUIRE(flags[p] != nullptr || (!do_signal && p != rank), "null flag row");
+    s.flags[p] = flags[p];
+  }
+  s.n_out = world; s.rank = rank; s.epoch = epoch; s.status = status; s.timeout_ns = peer_timeout_ns();
+  peer_sync_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(s, do_signal, do_wait);
+  LA3D_CUDA(cudaGetLastError());
+  return LA3D_OK;
 }
 }  // namespace la3d
+
+extern "C" void la3d_set_peer_timeout_ms(long long ms) { la3d::g_peer_timeout_ms = ms > 0 ? ms : 120000; }
 
 extern "C" int la3d_fit_boxes(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
                               int I, int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
                               uint32_t image_offset, void* workspace, size_t workspace_bytes, void* records,
                               int rec_f64, la3d_stream_t stream) {
-  return la3d::fit_boxes_multi(depth, masks, K, ground, B, I, H, W, mask_is_01, method, yaw_steps, seed, image_offset,
-                               workspace, workspace_bytes, &records, 1, rec_f64, nullptr, stream);
+  using namespace la3d;
+  LA3D_REQUIRE(records, "null pointer");
+  return fit_boxes_sink(depth, masks, K, ground, B, I, H, W, mask_is_01, method, yaw_steps, seed, image_offset,
+                        workspace, workspace_bytes, local_sink(records, rec_f64), stream);
+}
+
+extern "C" int la3d_fit_boxes_to(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
+                                 int I, int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
+                                 uint32_t image_offset, void* workspace, size_t workspace_bytes, const la3d_sink* sink,
+                                 la3d_stream_t stream) {
+  using namespace la3d;
+  RecordSink rs;
+  if (int rc = sink_from_public(sink, &rs)) return rc;
+  return fit_boxes_sink(depth, masks, K, ground, B, I, H, W, mask_is_01, method, yaw_steps, seed, image_offset,
+                        workspace, workspace_bytes, rs, stream);
 }
 
 // ---- the path from bit planes (no byte masks): annotations decoded on the device, or planes kept from an earlier scan
@@ -182,13 +248,12 @@ extern "C" int la3d_fit_boxes_bits(const float* depth, const uint32_t* bits, con
   return la3d_fit_scanned(depth, w.prep, bits, chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, records, rec_f64, stream);
 }
 
-extern "C" int la3d_fit_boxes_rle(const float* depth, const uint32_t* run_counts, const int64_t* run_offsets, int max_runs,
-                                  uint32_t* ends_ws, const double* K, const double* ground, int B, int I, int H, int W,
-                                  int method, int yaw_steps, uint32_t seed, uint32_t image_offset, void* workspace,
-                                  size_t workspace_bytes, int32_t* rle_status, void* records, int rec_f64,
-                                  la3d_stream_t stream) {
-  using namespace la3d;
-  LA3D_REQUIRE(depth && run_counts && run_offsets && K && workspace && rle_status && records, "null pointer");
+namespace la3d {
+static int fit_boxes_rle_sink(const float* depth, const uint32_t* run_counts, const int64_t* run_offsets, int max_runs,
+                              uint32_t* ends_ws, const double* K, const double* ground, int B, int I, int H, int W,
+                              int method, int yaw_steps, uint32_t seed, uint32_t image_offset, void* workspace,
+                              size_t workspace_bytes, int32_t* rle_status, const RecordSink& sink, la3d_stream_t stream) {
+  LA3D_REQUIRE(depth && run_counts && run_offsets && K && workspace && rle_status, "null pointer");
   LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE(I <= 8192, "at most 8192 instances per image");
   LA3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
@@ -205,16 +270,39 @@ extern "C" int la3d_fit_boxes_rle(const float* depth, const uint32_t* run_counts
   if (rc) return rc;
   rc = launch_sample(w.chunk_counts, pv, B, I, (int)la3d_chunks_per_plane(H, W), w.counts, w.ranks, s, false);
   if (rc) return rc;
-  void* rec = records;
-  return fit_scanned_multi(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, &rec, 1, rec_f64, s, false);
+  return fit_scanned_sink(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, sink, s, false);
+}
+}  // namespace la3d
+
+extern "C" int la3d_fit_boxes_rle(const float* depth, const uint32_t* run_counts, const int64_t* run_offsets, int max_runs,
+                                  uint32_t* ends_ws, const double* K, const double* ground, int B, int I, int H, int W,
+                                  int method, int yaw_steps, uint32_t seed, uint32_t image_offset, void* workspace,
+                                  size_t workspace_bytes, int32_t* rle_status, void* records, int rec_f64,
+                                  la3d_stream_t stream) {
+  using namespace la3d;
+  LA3D_REQUIRE(records, "null pointer");
+  return fit_boxes_rle_sink(depth, run_counts, run_offsets, max_runs, ends_ws, K, ground, B, I, H, W, method, yaw_steps,
+                            seed, image_offset, workspace, workspace_bytes, rle_status, local_sink(records, rec_f64), stream);
+}
+
+extern "C" int la3d_fit_boxes_rle_to(const float* depth, const uint32_t* run_counts, const int64_t* run_offsets,
+                                     int max_runs, uint32_t* ends_ws, const double* K, const double* ground, int B, int I,
+                                     int H, int W, int method, int yaw_steps, uint32_t seed, uint32_t image_offset,
+                                     void* workspace, size_t workspace_bytes, int32_t* rle_status, const la3d_sink* sink,
+                                     la3d_stream_t stream) {
+  using namespace la3d;
+  RecordSink rs;
+  if (int rc = sink_from_public(sink, &rs)) return rc;
+  return fit_boxes_rle_sink(depth, run_counts, run_offsets, max_runs, ends_ws, K, ground, B, I, H, W, method, yaw_steps,
+                            seed, image_offset, workspace, workspace_bytes, rle_status, rs, stream);
 }
 
 // ---- every masked pixel instead of the 500-point subsample: two launches (scan with the preparation CTAs, dense fit)
-extern "C" int la3d_fit_boxes_all(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
-                                  int I, int H, int W, int mask_is_01, void* workspace, size_t workspace_bytes,
-                                  void* records, int rec_f64, la3d_stream_t stream) {
-  using namespace la3d;
-  LA3D_REQUIRE(depth && masks && K && workspace && records, "null pointer");
+namespace la3d {
+static int fit_boxes_all_sink(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
+                              int I, int H, int W, int mask_is_01, int method, int yaw_steps, void* workspace,
+                              size_t workspace_bytes, const RecordSink& sink, la3d_stream_t stream) {
+  LA3D_REQUIRE(depth && masks && K && workspace, "null pointer");
   LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE(I <= 8192, "at most 8192 instances per image");
   LA3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
@@ -227,29 +315,37 @@ extern "C" int la3d_fit_boxes_all(const float* depth, const uint8_t* masks, cons
   const PrepArgs pa{K, ground, B, I, 0u, pv};              // cameras and ground rotations; the random words go unused
   int rc = launch_mask_scan(masks, B * I, H, W, mask_is_01, w.bits, w.chunk_counts, &pa, static_cast<cudaStream_t>(stream));
   if (rc) return rc;
-  return la3d_fit_all_points(depth, w.prep, w.bits, B, I, H, W, records, rec_f64, stream);
+  return fit_all_sink(depth, w.prep, w.bits, B, I, H, W, method, yaw_steps, sink, static_cast<cudaStream_t>(stream));
 }
+}  // namespace la3d
 
-extern "C" int la3d_fit_boxes_p2p(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
-                                  int I, int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
-                                  uint32_t image_offset, void* workspace, size_t workspace_bytes,
-                                  void* const* peer_records, int n_peers, int rec_f64, void* wait_before_fit,
-                                  la3d_stream_t stream) {
-  return la3d::fit_boxes_multi(depth, masks, K, ground, B, I, H, W, mask_is_01, method, yaw_steps, seed, image_offset,
-                               workspace, workspace_bytes, peer_records, n_peers, rec_f64, wait_before_fit, stream);
-}
-
-extern "C" int la3d_peer_barrier(uint32_t* const* flags, int rank, int world, uint32_t epoch, int* status,
-                                 la3d_stream_t stream) {
+extern "C" int la3d_fit_boxes_all(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
+                                  int I, int H, int W, int mask_is_01, void* workspace, size_t workspace_bytes,
+                                  void* records, int rec_f64, la3d_stream_t stream) {
   using namespace la3d;
-  LA3D_REQUIRE(flags, "null pointer");
-  LA3D_REQUIRE(world >= 1 && world <= LA3D_MAX_PEERS && rank >= 0 && rank < world, "bad rank / world");
-  PeerFlags pf{};
-  for (int p = 0; p < world; ++p) {
-    LA3D_REQUIRE(flags[p] != nullptr, "null flag array");
-    pf.flags[p] = flags[p];
-  }
-  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, rank, world, epoch, status);
-  LA3D_CUDA(cudaGetLastError());
-  return LA3D_OK;
+  LA3D_REQUIRE(records, "null pointer");
+  return fit_boxes_all_sink(depth, masks, K, ground, B, I, H, W, mask_is_01, LA3D_METHOD_PCA, 0, workspace,
+                            workspace_bytes, local_sink(records, rec_f64), stream);
+}
+
+extern "C" int la3d_fit_boxes_all_to(const float* depth, const uint8_t* masks, const double* K, const double* ground,
+                                     int B, int I, int H, int W, int mask_is_01, int method, int yaw_steps,
+                                     void* workspace, size_t workspace_bytes, const la3d_sink* sink, la3d_stream_t stream) {
+  using namespace la3d;
+  RecordSink rs;
+  if (int rc = sink_from_public(sink, &rs)) return rc;
+  return fit_boxes_all_sink(depth, masks, K, ground, B, I, H, W, mask_is_01, method, yaw_steps, workspace,
+                            workspace_bytes, rs, stream);
+}
+
+extern "C" int la3d_peer_signal(uint32_t* const* flags, int rank, int world, uint32_t epoch, la3d_stream_t stream) {
+  return la3d::peer_sync(flags, rank, world, epoch, nullptr, 1, 0, stream);
+}
+extern "C" int la3d_peer_wait(uint32_t* const* flags, int rank, int world, uint32_t epoch, int32_t* status,
+                              la3d_stream_t stream) {
+  return la3d::peer_sync(flags, rank, world, epoch, status, 0, 1, stream);
+}
+extern "C" int la3d_peer_barrier(uint32_t* const* flags, int rank, int world, uint32_t epoch, int32_t* status,
+                                 la3d_stream_t stream) {
+  return la3d::peer_sync(flags, rank, world, epoch, status, 1, 1, stream);
 }

@@ -22,7 +22,10 @@
 // No tensor cores: there is no dense contraction here.
 #include <math_constants.h>
 
+#include "box_tail.cuh"
 #include "common.cuh"
+#include "prep.cuh"
+#include "sink.cuh"
 
 namespace la3d {
 namespace {
@@ -50,18 +53,8 @@ struct FitArgs {
   const double* K;        // [images or boxes][9] intrinsics; may be null for explicit points
   const double* ground;   // [boxes][3] or null
   int method, yaw_steps, n_areas;
-  void* records[LA3D_MAX_PEERS];   // the record of box j goes to records[p] + j*64 for every p < n_out:
-  int n_out;                       // one local buffer, or the gathered buffers of all ranks (peer memory)
-  int rec_f64;
+  RecordSink sink;        // one local buffer, or the gathered buffers of all ranks (peer memory); sink.cuh
 };
-
-__device__ __forceinline__ void put_record(const FitArgs& a, size_t idx, double val) {
-#pragma unroll 1
-  for (int p = 0; p < a.n_out; ++p) {
-    if (a.rec_f64) reinterpret_cast<double*>(a.records[p])[idx] = val;
-    else reinterpret_cast<float*>(a.records[p])[idx] = (float)val;
-  }
-}
 
 // Static shared memory.  The y coordinate is not kept: only its minimum / maximum matter (they do
 // not depend on the yaw) and those are reduced on the fly.
@@ -541,17 +534,9 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   }
 
   if (status != LA3D_ST_OK) {                          // uniform across the CTA
-    for (int f = tid; f < LA3D_REC; f += kThreads) {
-      double val = CUDART_NAN;
-      if (f == LA3D_O_NVALID) val = (double)n_valid;
-      if (f == LA3D_O_STATUS) val = (double)status;
-      if (f == LA3D_O_NMASK) val = (double)n_src;
-      if (f == LA3D_O_PAD) val = 0.0;
-      put_record(a, (size_t)box * LA3D_REC + f, val);
-    }
-    return;
-  }
-
+    fill_failed_record(sm.rec, status, n_valid, n_src, kThreads);
+    __syncthreads();
+  } else {
   // ---- yaw ---------------------------------------------------------------------------
   bool have_trig = false;          // yaw_pca leaves cos / sin of the yaw in shared memory
   if (a.method == LA3D_METHOD_PCA) {
@@ -606,78 +591,11 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   const double dim[3] = {ext[3] - ext[0], ext[4] - ext[1], ext[5] - ext[2]};
   const double ctr[3] = {(ext[0] + ext[3]) / 2, (ext[1] + ext[4]) / 2, (ext[2] + ext[5]) / 2};
 
-  double* rec = sm.rec;
-  // rotate_y(-yaw) = [[c,0,-s],[0,1,0],[s,0,c]] with c = cos(yaw), s = sin(yaw)
-  const double Ry[9] = {cy_, 0.0, -sy_, 0.0, 1.0, 0.0, sy_, 0.0, cy_};
-  if (tid < 8) {
-    // convert_box_vertices(cx,cy,cz,dx,dy,dz,0).astype(float16)  (:71-103, :165)
-    const double sgx = (tid == 1 || tid == 2 || tid == 5 || tid == 6) ? 1.0 : -1.0;
-    const double sgy = (tid == 2 || tid == 3 || tid == 6 || tid == 7) ? 1.0 : -1.0;
-    const double sgz = (tid >= 4) ? 1.0 : -1.0;
-    const double lx = sgx * (dim[0] / 2), ly = sgy * (dim[1] / 2), lz = sgz * (dim[2] / 2);
-    // local @ rot(0)^T with rot(0) = [[1,0,0],[0,1,0],[-0,0,1]]: kept explicit for inf/NaN parity
-    double V[3];
-    V[0] = (lx * 1.0 + ly * 0.0 + lz * 0.0) + ctr[0];
-    V[1] = (lx * 0.0 + ly * 1.0 + lz * 0.0) + ctr[1];
-    V[2] = (lx * -0.0 + ly * 0.0 + lz * 1.0) + ctr[2];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) V[i] = (double)__half2float(__double2half(V[i]));
-    // vertices = (rotate_y(-yaw) @ V^T)^T @ Rg^T  (:168-169)
-    double v1[3], v2[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) v1[i] = Ry[i * 3] * V[0] + Ry[i * 3 + 1] * V[1] + Ry[i * 3 + 2] * V[2];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) v2[i] = v1[0] * sm.Rg[i * 3] + v1[1] * sm.Rg[i * 3 + 1] + v1[2] * sm.Rg[i * 3 + 2];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) rec[LA3D_O_VERT + tid * 3 + i] = v2[i];
-    // project_to_2d (util.py:227-229)
-    double uu = CUDART_NAN, vv = CUDART_NAN;
-    if (kScanned || a.K) {
-      const double h0 = sm.Kmat[0] * v2[0] + sm.Kmat[1] * v2[1] + sm.Kmat[2] * v2[2];
-      const double h1 = sm.Kmat[3] * v2[0] + sm.Kmat[4] * v2[1] + sm.Kmat[5] * v2[2];
-      const double h2 = sm.Kmat[6] * v2[0] + sm.Kmat[7] * v2[1] + sm.Kmat[8] * v2[2];
-      uu = h0 / h2; vv = h1 / h2;
-    }
-    rec[LA3D_O_UV + tid * 2] = uu;
-    rec[LA3D_O_UV + tid * 2 + 1] = vv;
-  } else if (tid == 32) {
-    // center_cam = Rg^T @ (rotate_y(-yaw) @ c)  (:172-173; Rg^T where the corners used Rg - kept)
-    double w[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) w[i] = Ry[i * 3] * ctr[0] + Ry[i * 3 + 1] * ctr[1] + Ry[i * 3 + 2] * ctr[2];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) rec[LA3D_O_CENTER + i] = sm.Rg[i] * w[0] + sm.Rg[3 + i] * w[1] + sm.Rg[6 + i] * w[2];
-    rec[LA3D_O_DIM] = dim[2]; rec[LA3D_O_DIM + 1] = dim[1]; rec[LA3D_O_DIM + 2] = dim[0];
-    rec[LA3D_O_YAW] = yaw;
-    rec[LA3D_O_NVALID] = (double)n_valid;
-    rec[LA3D_O_STATUS] = (double)LA3D_ST_OK;
-    rec[LA3D_O_NMASK] = (double)n_src;
-    rec[LA3D_O_PAD] = 0.0;
-  } else if (tid == 40) {
-    // R_cam = Rg^T @ rotate_y(-yaw)  (:176)
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        rec[LA3D_O_RCAM + i * 3 + k] = sm.Rg[i] * Ry[k] + sm.Rg[3 + i] * Ry[3 + k] + sm.Rg[6 + i] * Ry[6 + k];
+  write_box_record(dim, ctr, yaw, cy_, sy_, sm.Rg, sm.Kmat, kScanned || a.K != nullptr, sm.rec, n_valid, n_src, tid);
   }
-  __syncthreads();
-  if (tid == 0) {
-    // Python min()/max() over the 8 projections (combine_results.py:241-246): sequential
-    // `if x < m` / `if x > m`, so a leading NaN sticks and a later NaN is skipped.
-    double mnu = rec[LA3D_O_UV], mnv = rec[LA3D_O_UV + 1], mxu = mnu, mxv = mnv;
-    for (int j = 1; j < 8; ++j) {
-      const double uu = rec[LA3D_O_UV + 2 * j], vv = rec[LA3D_O_UV + 2 * j + 1];
-      if (uu < mnu) mnu = uu;
-      if (vv < mnv) mnv = vv;
-      if (uu > mxu) mxu = uu;
-      if (vv > mxv) mxv = vv;
-    }
-    rec[LA3D_O_BOX2D] = mnu; rec[LA3D_O_BOX2D + 1] = mnv;
-    rec[LA3D_O_BOX2D + 2] = mxu; rec[LA3D_O_BOX2D + 3] = mxv;
-  }
-  __syncthreads();
-  for (int f = tid; f < LA3D_REC; f += kThreads) put_record(a, (size_t)box * LA3D_REC + f, rec[f]);
+  sink_acquire(a.sink);
+  sink_store(a.sink, (size_t)box, sm.rec, kThreads);
+  sink_release(a.sink);
 }
 
 int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s, bool pdl = false) {
@@ -705,11 +623,10 @@ int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s, bool pdl = 
 }  // namespace la3d
 
 namespace la3d {
-int fit_scanned_multi(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
-                      const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
-                      void* const* records, int n_out, int rec_f64, cudaStream_t stream, bool pdl) {
-  LA3D_REQUIRE(depth && prep && bits && chunk_counts && ranks && records, "null pointer");
-  LA3D_REQUIRE(n_out >= 1 && n_out <= LA3D_MAX_PEERS, "between 1 and LA3D_MAX_PEERS output buffers");
+int fit_scanned_sink(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
+                     const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
+                     const RecordSink& sink, cudaStream_t stream, bool pdl) {
+  LA3D_REQUIRE(depth && prep && bits && chunk_counts && ranks, "null pointer");
   LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
   LA3D_REQUIRE(method != LA3D_METHOD_SWEEP || (yaw_steps > 0 && yaw_steps <= 16384), "sweep needs 1 <= yaw_steps <= 16384");
@@ -718,12 +635,8 @@ int fit_scanned_multi(const float* depth, const void* prep, const uint32_t* bits
   a.depth = depth; a.bits = bits; a.chunk_counts = chunk_counts; a.ranks = ranks;
   a.cams = pv.cams; a.Rg_pre = pv.Rg;
   a.I = I; a.HW = H * W; a.W = W; a.chunks = (int)la3d_chunks_per_plane(H, W);
-  a.method = method; a.yaw_steps = yaw_steps; a.rec_f64 = rec_f64;
-  for (int p = 0; p < n_out; ++p) {
-    LA3D_REQUIRE(records[p] != nullptr, "null output buffer");
-    a.records[p] = records[p];
-  }
-  a.n_out = n_out;
+  a.method = method; a.yaw_steps = yaw_steps;
+  a.sink = sink;
   return launch_fit(true, a, B * I, stream, pdl);
 }
 }  // namespace la3d
@@ -731,16 +644,20 @@ int fit_scanned_multi(const float* depth, const void* prep, const uint32_t* bits
 extern "C" int la3d_fit_scanned(const float* depth, const void* prep, const uint32_t* bits,
                                 const uint32_t* chunk_counts, const int32_t* ranks, int B, int I, int H, int W,
                                 int method, int yaw_steps, void* records, int rec_f64, la3d_stream_t stream) {
-  return la3d::fit_scanned_multi(depth, prep, bits, chunk_counts, ranks, B, I, H, W, method, yaw_steps, &records, 1,
-                                 rec_f64, static_cast<cudaStream_t>(stream), false);
+  using namespace la3d;
+  LA3D_REQUIRE(records, "null pointer");
+  return fit_scanned_sink(depth, prep, bits, chunk_counts, ranks, B, I, H, W, method, yaw_steps,
+                          local_sink(records, rec_f64), static_cast<cudaStream_t>(stream), false);
 }
 
-extern "C" int la3d_fit_scanned_p2p(const float* depth, const void* prep, const uint32_t* bits,
-                                    const uint32_t* chunk_counts, const int32_t* ranks, int B, int I, int H, int W,
-                                    int method, int yaw_steps, void* const* peer_records, int n_peers, int rec_f64,
-                                    la3d_stream_t stream) {
-  return la3d::fit_scanned_multi(depth, prep, bits, chunk_counts, ranks, B, I, H, W, method, yaw_steps, peer_records,
-                                 n_peers, rec_f64, static_cast<cudaStream_t>(stream), false);
+extern "C" int la3d_fit_scanned_to(const float* depth, const void* prep, const uint32_t* bits,
+                                   const uint32_t* chunk_counts, const int32_t* ranks, int B, int I, int H, int W,
+                                   int method, int yaw_steps, const la3d_sink* sink, la3d_stream_t stream) {
+  using namespace la3d;
+  RecordSink rs;
+  if (int rc = sink_from_public(sink, &rs)) return rc;
+  return fit_scanned_sink(depth, prep, bits, chunk_counts, ranks, B, I, H, W, method, yaw_steps, rs,
+                          static_cast<cudaStream_t>(stream), false);
 }
 
 extern "C" int la3d_fit_points(const double* pts, const int64_t* offsets, const int32_t* sample_idx, const double* K,
@@ -752,7 +669,7 @@ extern "C" int la3d_fit_points(const double* pts, const int64_t* offsets, const 
   LA3D_REQUIRE(method != LA3D_METHOD_SWEEP || (yaw_steps > 0 && yaw_steps <= 16384), "sweep needs 1 <= yaw_steps <= 16384");
   FitArgs a{};
   a.pts = pts; a.offsets = offsets; a.sample_idx = sample_idx;
-  a.K = K; a.ground = ground; a.method = method; a.yaw_steps = yaw_steps; a.records[0] = records; a.n_out = 1;
-  a.rec_f64 = rec_f64;
+  a.K = K; a.ground = ground; a.method = method; a.yaw_steps = yaw_steps;
+  a.sink = local_sink(records, rec_f64);
   return launch_fit(false, a, nboxes, static_cast<cudaStream_t>(stream));
 }

@@ -22,7 +22,10 @@
 
 #include <cstdlib>
 
+#include "box_tail.cuh"
 #include "common.cuh"
+#include "prep.cuh"
+#include "sink.cuh"
 
 namespace la3d {
 namespace {
@@ -37,17 +40,11 @@ struct AllArgs {
   const PrepCamera* cams;   // [images] intrinsics and their inverse (la3d_fit_prepare)
   const double* Rg_pre;     // [boxes][9] ground rotations (la3d_fit_prepare)
   int I, HW, W, words;      // words: bit words per plane (la3d_words_per_plane)
-  void* records;
-  int rec_f64;
+  RecordSink sink;          // sink.cuh
 };
 
 __device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }   // NaN in b is ignored
 __device__ __forceinline__ double dmax(double a, double b) { return b > a ? b : a; }
-
-__device__ __forceinline__ void put(const AllArgs& a, size_t idx, double val) {
-  if (a.rec_f64) reinterpret_cast<double*>(a.records)[idx] = val;
-  else reinterpret_cast<float*>(a.records)[idx] = (float)val;
-}
 
 struct Smem {
   double red[kWarps][8];
@@ -207,17 +204,9 @@ __global__ void __launch_bounds__(kThreads) fit_all_kernel(AllArgs a) {
   else if (inf_xz) status = LA3D_ST_NONFINITE;            // scikit-learn's input check raises
   else if (n_valid == 1) status = LA3D_ST_PCA_UNDEFINED;  // PCA(2) needs 2 samples
   if (status != LA3D_ST_OK) {                             // uniform across the CTA
-    for (int f = tid; f < LA3D_REC; f += kThreads) {
-      double val = CUDART_NAN;
-      if (f == LA3D_O_NVALID) val = (double)n_valid;
-      if (f == LA3D_O_STATUS) val = (double)status;
-      if (f == LA3D_O_NMASK) val = (double)n_src;
-      if (f == LA3D_O_PAD) val = 0.0;
-      put(a, (size_t)box * LA3D_REC + f, val);
-    }
-    return;
-  }
-
+    fill_failed_record(sm.rec, status, n_valid, n_src, kThreads);
+    __syncthreads();
+  } else {
   // ---- yaw: util_3dbox.py:181-186 with scikit-learn's arithmetic in closed form ----
   if (tid == 0) {
     const double n = (double)n_valid;
@@ -253,96 +242,45 @@ __global__ void __launch_bounds__(kThreads) fit_all_kernel(AllArgs a) {
   const double dim[3] = {ext[3] - ext[0], ext[4] - ext[1], ext[5] - ext[2]};
   const double ctr[3] = {(ext[0] + ext[3]) / 2, (ext[1] + ext[4]) / 2, (ext[2] + ext[5]) / 2};
 
-  // ---- tail (the arithmetic of fit.cu's kernel, util_3dbox.py:165-176, util.py:227-229) ----
-  double* rec = sm.rec;
-  // rotate_y(-yaw) = [[c,0,-s],[0,1,0],[s,0,c]] with c = cos(yaw), s = sin(yaw)
-  const double Ry[9] = {cy_, 0.0, -sy_, 0.0, 1.0, 0.0, sy_, 0.0, cy_};
-  if (tid < 8) {
-    // convert_box_vertices(cx,cy,cz,dx,dy,dz,0).astype(float16)  (:71-103, :165)
-    const double sgx = (tid == 1 || tid == 2 || tid == 5 || tid == 6) ? 1.0 : -1.0;
-    const double sgy = (tid == 2 || tid == 3 || tid == 6 || tid == 7) ? 1.0 : -1.0;
-    const double sgz = (tid >= 4) ? 1.0 : -1.0;
-    const double lx = sgx * (dim[0] / 2), ly = sgy * (dim[1] / 2), lz = sgz * (dim[2] / 2);
-    double V[3];
-    V[0] = (lx * 1.0 + ly * 0.0 + lz * 0.0) + ctr[0];
-    V[1] = (lx * 0.0 + ly * 1.0 + lz * 0.0) + ctr[1];
-    V[2] = (lx * -0.0 + ly * 0.0 + lz * 1.0) + ctr[2];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) V[i] = (double)__half2float(__double2half(V[i]));
-    // vertices = (rotate_y(-yaw) @ V^T)^T @ Rg^T  (:168-169)
-    double v1[3], v2[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) v1[i] = Ry[i * 3] * V[0] + Ry[i * 3 + 1] * V[1] + Ry[i * 3 + 2] * V[2];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) v2[i] = v1[0] * sm.Rg[i * 3] + v1[1] * sm.Rg[i * 3 + 1] + v1[2] * sm.Rg[i * 3 + 2];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) rec[LA3D_O_VERT + tid * 3 + i] = v2[i];
-    // project_to_2d (util.py:227-229)
-    const double h0 = sm.Kmat[0] * v2[0] + sm.Kmat[1] * v2[1] + sm.Kmat[2] * v2[2];
-    const double h1 = sm.Kmat[3] * v2[0] + sm.Kmat[4] * v2[1] + sm.Kmat[5] * v2[2];
-    const double h2 = sm.Kmat[6] * v2[0] + sm.Kmat[7] * v2[1] + sm.Kmat[8] * v2[2];
-    rec[LA3D_O_UV + tid * 2] = h0 / h2;
-    rec[LA3D_O_UV + tid * 2 + 1] = h1 / h2;
-  } else if (tid == 32) {
-    // center_cam = Rg^T @ (rotate_y(-yaw) @ c)  (:172-173; Rg^T where the corners used Rg - kept)
-    double w[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) w[i] = Ry[i * 3] * ctr[0] + Ry[i * 3 + 1] * ctr[1] + Ry[i * 3 + 2] * ctr[2];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) rec[LA3D_O_CENTER + i] = sm.Rg[i] * w[0] + sm.Rg[3 + i] * w[1] + sm.Rg[6 + i] * w[2];
-    rec[LA3D_O_DIM] = dim[2]; rec[LA3D_O_DIM + 1] = dim[1]; rec[LA3D_O_DIM + 2] = dim[0];
-    rec[LA3D_O_YAW] = yaw;
-    rec[LA3D_O_NVALID] = (double)n_valid;
-    rec[LA3D_O_STATUS] = (double)LA3D_ST_OK;
-    rec[LA3D_O_NMASK] = (double)n_src;
-    rec[LA3D_O_PAD] = 0.0;
-  } else if (tid == 40) {
-    // R_cam = Rg^T @ rotate_y(-yaw)  (:176)
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        rec[LA3D_O_RCAM + i * 3 + k] = sm.Rg[i] * Ry[k] + sm.Rg[3 + i] * Ry[3 + k] + sm.Rg[6 + i] * Ry[6 + k];
+  // ---- tail (box_tail.cuh: util_3dbox.py:165-176, util.py:227-229) ----
+  write_box_record(dim, ctr, yaw, cy_, sy_, sm.Rg, sm.Kmat, true, sm.rec, n_valid, n_src, tid);
   }
-  __syncthreads();
-  if (tid == 0) {
-    // Python min()/max() over the 8 projections (combine_results.py:241-246): sequential
-    // `if x < m` / `if x > m`, so a leading NaN sticks and a later NaN is skipped.
-    double mnu = rec[LA3D_O_UV], mnv = rec[LA3D_O_UV + 1], mxu = mnu, mxv = mnv;
-    for (int j = 1; j < 8; ++j) {
-      const double uu = rec[LA3D_O_UV + 2 * j], vv = rec[LA3D_O_UV + 2 * j + 1];
-      if (uu < mnu) mnu = uu;
-      if (vv < mnv) mnv = vv;
-      if (uu > mxu) mxu = uu;
-      if (vv > mxv) mxv = vv;
-    }
-    rec[LA3D_O_BOX2D] = mnu; rec[LA3D_O_BOX2D + 1] = mnv;
-    rec[LA3D_O_BOX2D + 2] = mxu; rec[LA3D_O_BOX2D + 3] = mxv;
-  }
-  __syncthreads();
-  for (int f = tid; f < LA3D_REC; f += kThreads) put(a, (size_t)box * LA3D_REC + f, rec[f]);
+  sink_acquire(a.sink);
+  sink_store(a.sink, (size_t)box, sm.rec, kThreads);
+  sink_release(a.sink);
 }
 
 }  // namespace
 }  // namespace la3d
 
-extern "C" int la3d_fit_all_points(const float* depth, const void* prep, const uint32_t* bits, int B, int I, int H, int W,
-                                   void* records, int rec_f64, la3d_stream_t stream) {
-  using namespace la3d;
-  LA3D_REQUIRE(depth && prep && bits && records, "null pointer");
+namespace la3d {
+int fit_all_sink(const float* depth, const void* prep, const uint32_t* bits, int B, int I, int H, int W, int method,
+                 int yaw_steps, const RecordSink& sink, cudaStream_t stream) {
+  LA3D_REQUIRE(depth && prep && bits, "null pointer");
   LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
   LA3D_REQUIRE(I <= 8192, "at most 8192 instances per image");
+  LA3D_REQUIRE(method == LA3D_METHOD_PCA, "the all-pixels fit supports method pca");
+  (void)yaw_steps;
   const PrepView pv = prep_view(const_cast<void*>(prep), B, I, prep_blocks(I));
   AllArgs a{};
   a.depth = depth; a.bits = bits; a.cams = pv.cams; a.Rg_pre = pv.Rg;
   a.I = I; a.HW = H * W; a.W = W; a.words = (int)la3d_words_per_plane(H, W);
-  a.records = records; a.rec_f64 = rec_f64;
+  a.sink = sink;
   // default: warp-cooperative walk of the set bits (lane = bit); LA3D_FITALL_VARIANT=0 selects the first form, one
   // thread per word (measured on B200, config 2: 0.86 ms vs 2.04 ms per step)
   const char* env = getenv("LA3D_FITALL_VARIANT");
-  if (!env || atoi(env) != 0) fit_all_kernel<true><<<(unsigned)(B * I), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  else fit_all_kernel<false><<<(unsigned)(B * I), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  if (!env || atoi(env) != 0) fit_all_kernel<true><<<(unsigned)(B * I), kThreads, 0, stream>>>(a);
+  else fit_all_kernel<false><<<(unsigned)(B * I), kThreads, 0, stream>>>(a);
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
+}
+}  // namespace la3d
+
+extern "C" int la3d_fit_all_points(const float* depth, const void* prep, const uint32_t* bits, int B, int I, int H, int W,
+                                   void* records, int rec_f64, la3d_stream_t stream) {
+  using namespace la3d;
+  LA3D_REQUIRE(records, "null pointer");
+  return fit_all_sink(depth, prep, bits, B, I, H, W, LA3D_METHOD_PCA, 0, local_sink(records, rec_f64),
+                      static_cast<cudaStream_t>(stream));
 }

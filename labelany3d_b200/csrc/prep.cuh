@@ -153,8 +153,11 @@ int launch_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes
                       uint32_t* ends_ws, uint32_t* bits, uint32_t* chunk_counts, int32_t* status, const PrepArgs* prep,
                       cudaStream_t s);
 
-int fit_scanned_multi(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
-                      const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
-                      void* const* records, int n_out, int rec_f64, cudaStream_t stream, bool pdl = false);
+struct RecordSink;
+int fit_scanned_sink(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
+                     const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
+                     const RecordSink& sink, cudaStream_t stream, bool pdl = false);
+int fit_all_sink(const float* depth, const void* prep, const uint32_t* bits, int B, int I, int H, int W, int method,
+                 int yaw_steps, const RecordSink& sink, cudaStream_t stream);
 
 }  // namespace la3d

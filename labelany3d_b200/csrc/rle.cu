@@ -309,12 +309,10 @@ int launch_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes
   const char* env = getenv("LA3D_RLE_VARIANT");
   const int variant = env ? atoi(env) : 0;
   auto launch = [&](auto kernel, int slot) -> int {
-    // opt in to more dynamic shared memory only when a launch needs more than any before it
-    static size_t opted[4] = {16 * 1024, 16 * 1024, 16 * 1024, 16 * 1024};
-    if (smem > opted[slot]) {
+    // the opt-in is per device and cheap: repeat it whenever a launch needs it (no process-wide cache)
+    (void)slot;
+    if (smem > 48 * 1024)
       LA3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      opted[slot] = smem;
-    }
     kernel<<<(unsigned)ctas, kThreads, smem, s>>>(a, pa);
     return LA3D_OK;
   };

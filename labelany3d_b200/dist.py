@@ -49,59 +49,29 @@ def all_gather_records(local, total=None, group=None):
     return out[:total]
 
 
-class ShardedBoxFitter:
-    """``BoxFitter`` for this rank's block of a ``B_total``-image batch plus the gather of the records.
+class PeerGather:
+    """The gathered record buffers of this rank in peer-mapped (symmetric) memory plus the flag rows: what a
+    box kernel needs to write its records into every rank's buffer and to synchronise with the peers itself
+    (``la3d_sink`` of include/la3d.h).  torch's symmetric memory is used for allocation and the handle
+    exchange only.  Two gathered buffers alternate: the tensor a step returns stays valid until the
+    next-but-one step (consume it on the stream that issues the steps)."""
 
-    ``collective="p2p"`` (default on CUDA with more than one rank): the gathered ``[world*per, I, 64]``
-    buffer of every rank lives in symmetric (peer-mapped) memory and the fit kernel of rank ``r``
-    writes its records directly into slot ``r`` of EVERY rank's buffer over NVLink
-    (``la3d_fit_boxes_p2p``); a flag barrier over peer memory (``la3d_peer_barrier``) then tells each
-    rank that all slots have landed.  No separate collective pass, no NCCL launch on the data path.
-    The gathered buffer is double-buffered: the tensor a call returns stays valid until the
-    next-but-one call (consume it on the same stream).
-    ``collective="nccl"``: one ``all_gather_into_tensor`` after the fit (the plain form).
-    """
-
-    def __init__(self, B_total, I, H, W, device=None, out_dtype=torch.float64, group=None, collective=None):
-        from .ops import BoxFitter
-        self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.B_total = int(B_total)
-        self.start, self.stop, self.per = shard_range(self.B_total, self.rank, self.world)
-        self.n_local = self.stop - self.start
-        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.device = torch.device(device)
-        self.out_dtype = out_dtype
-        self.I = int(I)
-        self.local = BoxFitter(max(self.n_local, 1), I, H, W, device=device, out_dtype=out_dtype)
-        if collective is None:
-            collective = "p2p" if self.world > 1 else "none"
-        if collective not in ("p2p", "nccl", "none"):
-            raise ValueError(f"collective must be 'p2p', 'nccl' or 'none', got {collective!r}")
-        if self.world == 1:
-            collective = "none"
-        self.collective = collective
-        if collective == "p2p":
-            self._init_p2p()
-        else:
-            self.gathered = torch.empty((self.world * self.per, I, REC), dtype=out_dtype, device=device)
-            self.slot = torch.full((self.per, I, REC), float("nan"), dtype=out_dtype, device=device)
-            self.slot[..., O_STATUS] = -1
-
-    # -- peer memory ---------------------------------------------------------------------------
-    def _init_p2p(self):
+    def __init__(self, per, I, world, rank, device, out_dtype, group=None):
         import torch.distributed._symmetric_memory as symm
         from . import _lib
-        if self.world > 8:
+        if world > _lib.MAX_PEERS:
             raise ValueError("the peer-memory gather supports at most 8 ranks (one NVLink node)")
-        grp = self.group if self.group is not None else dist.group.WORLD
+        self._lib_mod = _lib
+        self._lib = _lib.load()
+        self.world, self.rank, self.per, self.I = int(world), int(rank), int(per), int(I)
+        self.device, self.out_dtype = torch.device(device), out_dtype
+        grp = group if group is not None else dist.group.WORLD
         shape = (self.world * self.per, self.I, REC)
-        self._bufs, self._peer_slots = [], []
-        esize = torch.empty((), dtype=self.out_dtype).element_size()
+        esize = torch.empty((), dtype=out_dtype).element_size()
         slot_bytes = self.per * self.I * REC * esize
-        for _ in range(2):                                   # double buffer (see the class docstring)
-            t = symm.empty(shape, dtype=self.out_dtype, device=self.device)
+        self._bufs, self._peer_slots = [], []
+        for _ in range(2):
+            t = symm.empty(shape, dtype=out_dtype, device=self.device)
             t.fill_(float("nan"))
             t[..., O_STATUS] = -1
             hdl = symm.rendezvous(t, grp)
@@ -111,55 +81,143 @@ class ShardedBoxFitter:
         f.zero_()
         fh = symm.rendezvous(f, grp)
         self._flags, self._flag_hdl = f, fh
-        self._flag_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in fh.buffer_ptrs])
-        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self._side = torch.cuda.Stream(device=self.device)
-        self._ev_fit = torch.cuda.Event()
-        self._ev_bar = [torch.cuda.Event(), torch.cuda.Event()]
-        self._epoch = 0
-        self._lib = _lib.load()
+        self._flag_list = [int(p) for p in fh.buffer_ptrs]
+        self._flag_ptrs = (ctypes.c_void_p * self.world)(*self._flag_list)
+        self._counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # sticky error word in pinned host memory: readable without a device synchronisation, even after a trap
+        self._status = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.epoch = 0
         torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)                       # every rank's fills have landed before the first step
+        dist.barrier(group=group)                            # every rank's fills have landed before the first step
+
+    def next_sink(self):
+        """Advance the epoch; returns ``(sink, gathered_buffer)`` of the new step."""
+        self.epoch += 1
+        e = self.epoch
+        sink = self._lib_mod.make_sink(self._peer_slots[e & 1], self.out_dtype == torch.float64, self._flag_list,
+                                       self._counter.data_ptr(), self._status.data_ptr(), e, self.rank)
+        return sink, self._bufs[e & 1][0]
+
+    def signal(self):
+        """For a rank without images in this step: publish the epoch without a fit."""
+        with torch.cuda.device(self.device):
+            rc = self._lib.la3d_peer_signal(self._flag_ptrs, self.rank, self.world, self.epoch & 0xFFFFFFFF,
+                                            torch.cuda.current_stream().cuda_stream)
+        self._lib_mod.check(rc, "la3d_peer_signal")
+
+    def wait(self):
+        """The current stream waits until the records of the last step have landed from every rank."""
+        if self.epoch:
+            with torch.cuda.device(self.device):
+                rc = self._lib.la3d_peer_wait(self._flag_ptrs, self.rank, self.world, self.epoch & 0xFFFFFFFF,
+                                              self._status.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            self._lib_mod.check(rc, "la3d_peer_wait")
+
+    def check(self):
+        """Raises if a peer failed to arrive within the timeout (no device synchronisation: the word is in
+        pinned host memory and is written before the kernel traps)."""
+        if int(self._status[0]) != 0:
+            raise RuntimeError("la3d peer synchronisation: a peer did not arrive within the timeout "
+                               "(LA3D_PEER_TIMEOUT_MS); the gathered records are not valid")
+
+
+class ShardedBoxFitter:
+    """``BoxFitter`` (or ``RleBoxFitter`` / the all-pixels fit) for this rank's block of a ``B_total``-image
+    batch plus the gather of the records.
+
+    ``collective="p2p"`` (default on CUDA with more than one rank): the gathered ``[world*per, I, 64]``
+    buffer of every rank lives in symmetric (peer-mapped) memory and the fit kernel of rank ``r``
+    writes its records directly into slot ``r`` of EVERY rank's buffer over NVLink
+    (``la3d_fit_boxes_to``).  The cross-GPU synchronisation is inside the same kernel (flag rows in peer
+    memory: acquire before the first store, release by the last CTA), so a step adds no launch, no
+    side stream and no NCCL call to the data path; a consumer waits with :meth:`wait_gathered`
+    (``wait=True`` does it in the call).  The gathered buffer is double-buffered: the tensor a call
+    returns stays valid until the next-but-one call (consume it on the same stream).
+    ``collective="nccl"``: one ``all_gather_into_tensor`` after the fit (the plain form).
+    ``source``: ``"masks"`` (byte masks, the default), ``"rle"`` (COCO run-length annotations:
+    ``total_runs`` / ``max_runs`` size the plan; call with ``(depth, K, (run_counts, run_offsets), ground, ...)``)
+    or ``"all"`` (every masked pixel instead of the random 500).
+    """
+
+    def __init__(self, B_total, I, H, W, device=None, out_dtype=torch.float64, group=None, collective=None,
+                 source="masks", total_runs=0, max_runs=0):
+        from . import ops
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.B_total = int(B_total)
+        self.start, self.stop, self.per = shard_range(self.B_total, self.rank, self.world)
+        self.n_local = self.stop - self.start
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.out_dtype = out_dtype
+        self.I, self.H, self.W = int(I), int(H), int(W)
+        if source not in ("masks", "rle", "all"):
+            raise ValueError(f"source must be 'masks', 'rle' or 'all', got {source!r}")
+        self.source = source
+        nb = max(self.n_local, 1)
+        if source == "rle":
+            self.local = ops.RleBoxFitter(nb, I, H, W, total_runs, max_runs, device=device, out_dtype=out_dtype)
+        elif source == "all":
+            self.local = None
+            self._ws = torch.empty(int(ops._lib.load().la3d_fit_workspace_bytes(nb, I, H, W)), dtype=torch.uint8,
+                                   device=self.device)
+        else:
+            self.local = ops.BoxFitter(nb, I, H, W, device=device, out_dtype=out_dtype)
+        if collective is None:
+            collective = "p2p" if self.world > 1 else "none"
+        if collective not in ("p2p", "nccl", "none"):
+            raise ValueError(f"collective must be 'p2p', 'nccl' or 'none', got {collective!r}")
+        if self.world == 1:
+            collective = "none"
+        self.collective = collective
+        if collective == "p2p":
+            self.peers = PeerGather(self.per, I, self.world, self.rank, self.device, out_dtype, group)
+        else:
+            self.peers = None
+            self.gathered = torch.empty((self.world * self.per, I, REC), dtype=out_dtype, device=device)
+            self.slot = torch.full((self.per, I, REC), float("nan"), dtype=out_dtype, device=device)
+            self.slot[..., O_STATUS] = -1
 
     def wait_gathered(self):
         """Make the current stream wait until the records of the last call have landed on every rank."""
-        if self.collective == "p2p" and self._epoch:
-            torch.cuda.current_stream(self.device).wait_event(self._ev_bar[self._epoch & 1])
+        if self.peers is not None:
+            self.peers.wait()
 
     def check_barrier_status(self):
-        """Raises if a peer failed to arrive at a barrier (synchronises the device)."""
-        if self.collective == "p2p" and int(self._status.item()) != 0:
-            raise RuntimeError("la3d_peer_barrier: a peer did not arrive within the timeout")
+        """Raises if a peer failed to arrive at a synchronisation point within the timeout."""
+        if self.peers is not None:
+            self.peers.check()
+
+    def _fit_local(self, depth, K, masks, ground, method, yaw_steps, seed, out=None, sink=None, events=None):
+        if self.source == "rle":
+            run_counts, run_offsets = masks
+            return self.local(depth, K, run_counts, run_offsets, ground, method, yaw_steps, seed, image_offset=self.start,
+                              out=out, sink=sink)
+        if self.source == "all":
+            from . import ops
+            if sink is None:
+                sink = ops._lib.make_sink([out.data_ptr()], self.out_dtype == torch.float64)
+            return ops.fit_boxes_all(depth, K, masks, ground, self.out_dtype, method, yaw_steps, sink=sink, workspace=self._ws)
+        return self.local(depth, K, masks, ground, method, yaw_steps, seed, image_offset=self.start, out=out, sink=sink,
+                          events=events)
 
     def __call__(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, events=None, wait=True):
         """Inputs are this rank's block (``[n_local, ...]``).  Returns ``[B_total, I, 64]`` on every rank.
-        ``wait=False`` (p2p only): do not make the current stream wait for the peer barrier; the result is
-        complete once :meth:`wait_gathered` (or a device synchronisation) has passed."""
-        if self.collective == "p2p":
-            from . import _lib
-            self._epoch += 1
-            e = self._epoch
-            buf, _ = self._bufs[e & 1]
-            cur = torch.cuda.current_stream(self.device)
+        ``wait=False`` (p2p only): do not make the current stream wait for the peers' records; the result is
+        complete once :meth:`wait_gathered` has been enqueued before its consumer."""
+        if self.peers is not None:
+            self.peers.check()                               # a lost peer is fatal, never stale records
+            sink, buf = self.peers.next_sink()
             if self.n_local:
-                # the fit may write the peers' buffer e&1 once every rank is past step e-1 (previous barrier)
-                self.local(depth, K, masks, ground, method, yaw_steps, seed, image_offset=self.start,
-                           peers=self._peer_slots[e & 1], wait_before_fit=self._ev_bar[(e - 1) & 1] if e > 1 else None)
-            elif e > 1:
-                cur.wait_event(self._ev_bar[(e - 1) & 1])
-            self._ev_fit.record(cur)
-            self._side.wait_event(self._ev_fit)
-            with torch.cuda.device(self.device):
-                rc = self._lib.la3d_peer_barrier(self._flag_ptrs, self.rank, self.world, e & 0xFFFFFFFF,
-                                                 self._status.data_ptr(), self._side.cuda_stream)
-            _lib.check(rc, "la3d_peer_barrier")
-            self._ev_bar[e & 1].record(self._side)
+                self._fit_local(depth, K, masks, ground, method, yaw_steps, seed, sink=sink)
+            else:
+                self.peers.signal()
             if wait:
-                cur.wait_event(self._ev_bar[e & 1])
+                self.peers.wait()
             return buf[:self.B_total]
         if self.n_local:
-            self.local(depth, K, masks, ground, method, yaw_steps, seed, image_offset=self.start,
-                       out=self.slot[:self.n_local], events=events)
+            self._fit_local(depth, K, masks, ground, method, yaw_steps, seed, out=self.slot[:self.n_local], events=events)
         if self.world == 1:
             return self.slot[:self.B_total]
         dist.all_gather_into_tensor(self.gathered, self.slot, group=self.group)

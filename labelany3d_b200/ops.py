@@ -279,15 +279,14 @@ class BoxFitter:
         self.records = torch.empty((B, I, REC), dtype=out_dtype, device=self.device)
 
     def __call__(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0, out=None,
-                 events=None, peers=None, wait_before_fit=None):
+                 events=None, sink=None):
         """Fit every (image, instance) box; returns ``records[B,I,64]`` (a buffer owned by the plan
         unless ``out`` is given).  ``events``: optional list of 5 ``torch.cuda.Event``; the four kernels
         are then issued one after the other on the current stream (no overlap) with the events
         recorded before, between and after them: prepare, scan, sample, fit (per-kernel timing
-        without a profiler).  ``peers``: list of device pointers (ints) of ``[B,I,64]`` slots in
-        peer-mapped record buffers; the fit kernel then writes every record to all of them
-        (``la3d_fit_boxes_p2p``) instead of to ``out``; ``wait_before_fit``: a ``torch.cuda.Event`` the
-        stream waits for between the sampler and the fit kernel (the previous step's peer barrier)."""
+        without a profiler).  ``sink``: a ``_lib.Sink`` (``la3d_sink``): the fit kernel then writes every
+        record to all its destinations, e.g. this rank's slot in the peer-mapped gathered buffer of every
+        rank, and synchronises with the peers itself (``la3d_fit_boxes_to``) instead of writing ``out``."""
         B, I, H, W = self.shape
         # the fit gathers only 500 depth values per box, so the depth maps may stay in pinned host memory
         depth = _need_cuda("depth", depth, torch.float32, pinned_ok=True)
@@ -308,16 +307,14 @@ class BoxFitter:
         lib = self.lib
         with torch.cuda.device(self.device):
             st = _stream()
-            if peers is not None:
+            if sink is not None:
                 if events is not None:
-                    raise ValueError("events and peers are mutually exclusive")
-                arr = (ctypes.c_void_p * len(peers))(*peers)
-                rc = lib.la3d_fit_boxes_p2p(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01,
-                                            _method_id(method), int(yaw_steps), int(seed) & 0xFFFFFFFF,
-                                            int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace), self.ws_bytes,
-                                            arr, len(peers), f64,
-                                            None if wait_before_fit is None else wait_before_fit.cuda_event, st)
-                _lib.check(rc, "la3d_fit_boxes_p2p")
+                    raise ValueError("events and sink are mutually exclusive")
+                rc = lib.la3d_fit_boxes_to(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01,
+                                           _method_id(method), int(yaw_steps), int(seed) & 0xFFFFFFFF,
+                                           int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace), self.ws_bytes,
+                                           ctypes.byref(sink), st)
+                _lib.check(rc, "la3d_fit_boxes_to")
             elif events is None:
                 rc = lib.la3d_fit_boxes(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01,
                                         _method_id(method), int(yaw_steps), int(seed) & 0xFFFFFFFF,
@@ -476,7 +473,8 @@ def fit_boxes_bits(depth, K, bits, chunk_counts, I, ground=None, method="pca", y
     return rec
 
 
-def fit_boxes_all(depth, K, masks, ground=None, out_dtype=torch.float64):
+def fit_boxes_all(depth, K, masks, ground=None, out_dtype=torch.float64, method="pca", yaw_steps=0, sink=None,
+                  workspace=None):
     """Boxes from EVERY masked pixel (``la3d_fit_boxes_all``): the reference's ``estimate_bbox`` with
     ``method='pca'`` and its random 500-point draw (``src/util_3dbox.py:123-125``) replaced by the identity.
     Deterministic, no generator involved; same record layout and status codes as :func:`fit_boxes`.
@@ -498,12 +496,17 @@ def fit_boxes_all(depth, K, masks, ground=None, out_dtype=torch.float64):
     m8, is01 = _masks_u8(masks)
     dev = depth.device
     ws_bytes = int(lib.la3d_fit_workspace_bytes(B, I, H, W))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    rec = torch.empty((B, I, REC), dtype=out_dtype, device=dev)
+    ws = workspace if workspace is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if ws.numel() < ws_bytes:
+        raise ValueError("workspace too small")
+    rec = None
+    if sink is None:
+        rec = torch.empty((B, I, REC), dtype=out_dtype, device=dev)
+        sink = _lib.make_sink([rec.data_ptr()], out_dtype == torch.float64)
     with torch.cuda.device(dev):
-        rc = lib.la3d_fit_boxes_all(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01, _ptr(ws), ws_bytes,
-                                    _ptr(rec), int(out_dtype == torch.float64), _stream())
-    _lib.check(rc, "la3d_fit_boxes_all")
+        rc = lib.la3d_fit_boxes_all_to(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01, _method_id(method),
+                                       int(yaw_steps), _ptr(ws), ws_bytes, ctypes.byref(sink), _stream())
+    _lib.check(rc, "la3d_fit_boxes_all_to")
     return rec
 
 
@@ -544,8 +547,9 @@ class RleBoxFitter:
         self.records = torch.empty((B, I, REC), dtype=out_dtype, device=self.device)
 
     def __call__(self, depth, K, run_counts, run_offsets, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0,
-                 out=None):
-        """Returns ``records[B,I,64]``; ``self.rle_status[B*I]`` holds the decoder's per-plane status."""
+                 out=None, sink=None):
+        """Returns ``records[B,I,64]``; ``self.rle_status[B*I]`` holds the decoder's per-plane status.
+        ``sink``: as for :class:`BoxFitter` (``la3d_fit_boxes_rle_to``)."""
         B, I, H, W = self.shape
         depth = _need_cuda("depth", depth, torch.float32, pinned_ok=True)
         K = _need_cuda("K", K, torch.float64)
@@ -563,13 +567,15 @@ class RleBoxFitter:
                 raise ValueError(f"ground must be [{B},{I},3]")
         rec = self.records if out is None else _need_cuda("out", out, self.out_dtype)
         counts_ptr = _ptr(run_counts) if run_counts.numel() else _ptr(self.ends_ws)
+        if sink is None:
+            sink = _lib.make_sink([rec.data_ptr()], self.out_dtype == torch.float64)
         with torch.cuda.device(self.device):
-            rc = self.lib.la3d_fit_boxes_rle(_ptr(depth), counts_ptr, _ptr(run_offsets), self.max_runs, _ptr(self.ends_ws),
-                                             _ptr(K), _ptr(ground), B, I, H, W, _method_id(method), int(yaw_steps),
-                                             int(seed) & 0xFFFFFFFF, int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace),
-                                             self.ws_bytes, _ptr(self.rle_status), _ptr(rec),
-                                             int(self.out_dtype == torch.float64), _stream())
-        _lib.check(rc, "la3d_fit_boxes_rle")
+            rc = self.lib.la3d_fit_boxes_rle_to(_ptr(depth), counts_ptr, _ptr(run_offsets), self.max_runs, _ptr(self.ends_ws),
+                                                _ptr(K), _ptr(ground), B, I, H, W, _method_id(method), int(yaw_steps),
+                                                int(seed) & 0xFFFFFFFF, int(image_offset) & 0xFFFFFFFF,
+                                                _ptr(self.workspace), self.ws_bytes, _ptr(self.rle_status),
+                                                ctypes.byref(sink), _stream())
+        _lib.check(rc, "la3d_fit_boxes_rle_to")
         return rec
 
 

@@ -39,7 +39,7 @@ def test_library_exports_every_header_symbol():
     lib = ctypes.CDLL(path)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().la3d_version() == 100
+    assert _lib.load().la3d_version() == 200
     # layout helpers are pure host functions
     assert _lib.load().la3d_chunks_per_plane(480, 640) == 600
     assert _lib.load().la3d_words_per_plane(480, 640) == 9600
@@ -62,8 +62,13 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
         "la3d_sample_ranks": lambda: lib.la3d_sample_ranks(None, None, 1, 1, 4, 4, None, None, None),
         "la3d_fit_scanned": lambda: lib.la3d_fit_scanned(None, None, None, None, None, 1, 1, 4, 4, 0, 0, None, 0, None),
         "la3d_fit_boxes": lambda: lib.la3d_fit_boxes(None, None, None, None, 1, 1, 4, 4, 1, 0, 0, 0, 0, None, 0, None, 0, None),
-        "la3d_fit_boxes_p2p": lambda: lib.la3d_fit_boxes_p2p(None, None, None, None, 1, 1, 4, 4, 1, 0, 0, 0, 0, None, 0, None, 1, 0, None, None),
+        "la3d_fit_boxes_to": lambda: lib.la3d_fit_boxes_to(None, None, None, None, 1, 1, 4, 4, 1, 0, 0, 0, 0, None, 0, None, None),
+        "la3d_fit_scanned_to": lambda: lib.la3d_fit_scanned_to(None, None, None, None, None, 1, 1, 4, 4, 0, 0, None, None),
+        "la3d_fit_boxes_rle_to": lambda: lib.la3d_fit_boxes_rle_to(None, None, None, 0, None, None, None, 1, 1, 4, 4, 0, 0, 0, 0, None, 0, None, None, None),
+        "la3d_fit_boxes_all_to": lambda: lib.la3d_fit_boxes_all_to(None, None, None, None, 1, 1, 4, 4, 1, 0, 0, None, 0, None, None),
         "la3d_peer_barrier": lambda: lib.la3d_peer_barrier(None, 0, 1, 1, None, None),
+        "la3d_peer_signal": lambda: lib.la3d_peer_signal(None, 0, 1, 1, None),
+        "la3d_peer_wait": lambda: lib.la3d_peer_wait(None, 0, 1, 1, None, None),
         "la3d_fit_points": lambda: lib.la3d_fit_points(None, None, None, None, None, 1, 0, 0, None, 0, None),
         "la3d_project_points": lambda: lib.la3d_project_points(None, None, None, 1, None, None),
         "la3d_iou_matrix": lambda: lib.la3d_iou_matrix(None, None, None, None, None, 1, None, None),
@@ -85,6 +90,12 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
     assert lib.la3d_depth_lift(p, p, 5, 0, None, None, 1, 4, 4, p, 0, None) == EINVAL and b"k_stride" in lib.la3d_last_error()
     assert lib.la3d_fit_scanned(p, p, p, p, p, 1, 1, 4, 4, 2, 0, p, 0, None) == EINVAL and b"yaw_steps" in lib.la3d_last_error()
     assert lib.la3d_peer_barrier(ctypes.cast(p, ctypes.c_void_p), 3, 2, 1, None, None) == EINVAL
+    # sinks: destinations, alignment, the synchronisation block
+    from labelany3d_b200 import _lib as L
+    bad = [L.make_sink([], 0), L.make_sink([p + 4], 0), L.make_sink([p], 0, flags=[p], counter=None, status=None, epoch=1),
+           L.make_sink([p], 0, flags=[p], counter=p, status=None, epoch=0), L.make_sink([p, p], 0, flags=[p, p], counter=p, epoch=1, rank=2)]
+    for sink in bad:
+        assert lib.la3d_fit_boxes_to(p, p, p, None, 1, 1, 4, 4, 1, 0, 0, 0, 0, p, 1 << 20, ctypes.byref(sink), None) == EINVAL
     assert lib.la3d_prep_bytes(0, 4) == 0 and lib.la3d_fit_workspace_bytes(1, 0, 4, 4) == 0
     assert lib.la3d_prep_bytes(256, 8) > 256 * 8 * 1024 * 4
 

@@ -15,7 +15,8 @@ depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=3, device="cuda")
 lib = _lib.load()
 m8 = masks.view(torch.uint8)
 slots = [ops.BoxFitter(B, I, H, W, out_dtype=torch.float32) for _ in range(2)]
-s_scan, s_fit = torch.cuda.Stream(), torch.cuda.Stream()
+prio = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # -1: the sampler / fit stream gets the higher priority
+s_scan, s_fit = torch.cuda.Stream(), torch.cuda.Stream(priority=prio)
 N = 8
 E = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 ev = [{k: E() for k in ("scan0", "scan1", "prep1", "samp0", "samp1", "fit1")} for _ in range(N)]
@@ -48,7 +49,7 @@ for rep in range(2):          # first repetition warms up
         e["fit1"].record(s_fit)
         done[k & 1] = e["fit1"]
     torch.cuda.synchronize()
-print(f"ctas={ctas} stages={stages}: microseconds since start")
+print(f"ctas={ctas} stages={stages} tail-stream priority={prio}: microseconds since start")
 for k in range(N):
     e = ev[k]
     us = {n: t0.elapsed_time(x) * 1e3 for n, x in e.items()}
