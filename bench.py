@@ -79,7 +79,7 @@ def config_dict(args, collective="p2p"):
     G = global_batch(args)
     how = {"p2p": ", records written by the fit kernel into every rank's gathered buffer over NVLink peer memory, the "
                   "cross-GPU flags handled inside the same kernel, each step",
-           "nccl": ", NCCL all-gather of the packed records each step"}[collective]
+           "nccl": ", NCCL all-gather of the packed records each step"}.get(collective, "")
     what = (f"fixed global batch of {G} images (BASELINE configs[2]'s sharded batch; = {G // WEAK_BATCH} x configs[1]'s batch), "
             if args.scaling == "strong" else f"{WEAK_BATCH} images per GPU (BASELINE configs[1] per GPU), ")
     return {"workload": what + f"BASELINE configs[1] shape: {w['W']}x{w['H']} depth, {w['I']} instances/image, "
