@@ -180,6 +180,12 @@ int la3d_fit_scanned(const float* depth, const void* prep, const uint32_t* bits,
  * mask scan's launch (B extra CTAs at the front of its grid, so the latency-bound seeding hides
  * under the HBM-bound scan), then la3d_sample_ranks and la3d_fit_scanned.  `workspace` needs
  * la3d_fit_workspace_bytes() bytes, 256-byte aligned. */
+/* Optional pipeline over parts of a batch (LA3D_PIPE_IMAGES=n or la3d_set_pipeline_images(n): n images per part,
+ * 0 = never split = the default, -1 = back to the environment's choice): the scan of part p+1 on `stream` overlaps
+ * the sampler and fit of part p on internal high-priority streams that fork from and join back into `stream`
+ * (events only; the call stays asynchronous and graph-capturable).  Results do not depend on the split.  Off by
+ * default because it measured slower on B200. */
+void la3d_set_pipeline_images(int images_per_part);
 size_t la3d_fit_workspace_bytes(int B, int I, int H, int W);
 int la3d_fit_boxes(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
                    int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed, uint32_t image_offset,

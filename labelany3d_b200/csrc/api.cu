@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include "prep.cuh"
 #include "sink.cuh"
 
@@ -121,6 +122,112 @@ int sink_from_public(const la3d_sink* pub, RecordSink* out) {
   return LA3D_OK;
 }
 
+// ---- the step as a pipeline over parts of the batch ------------------------------------------
+// The mask scan (or the run-length decode) is the HBM-bound pass; the sampler and the fit that follow are
+// latency- and issue-bound tails that need nothing from the NEXT images.  A batch of more than one part is
+// therefore cut along the image axis: the scan of part p+1 runs on the caller's stream while the sampler and
+// the fit of part p run on a high-priority side stream (two of them, alternating, so that the tails of two
+// parts may also overlap each other).  The side streams fork from and join back into the caller's stream with
+// events, so the call is still "asynchronous on `stream`" and can be captured into a CUDA graph.
+// Measured on B200 (profiles/r2_f_pipe_sweep.json; 2048 images x 8 masks, 36-step sweep): unsplit 1350 us, parts of
+// 512 / 256 / 128 / 64 images 1456 / 1502 / 1497 / 1806 us - the scan holds every thread slot and register of an SM
+// (8 CTAs x 256 threads x 32 registers), so a resident fit CTA displaces scan CTAs and the loads of the latency-bound
+// fit queue behind a saturated HBM; both kernels lose more than the overlap wins.  The split is therefore OFF by
+// default: LA3D_PIPE_IMAGES = images per part (default 0 = never split) or la3d_set_pipeline_images().
+constexpr int kMaxParts = 32;
+struct Pipe {
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t scanned[kMaxParts] = {};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  bool ready = false;
+  std::mutex mu;
+};
+static Pipe g_pipes[64];
+
+static int pipe_images() {
+  static const int v = getenv("LA3D_PIPE_IMAGES") ? atoi(getenv("LA3D_PIPE_IMAGES")) : 0;
+  return v;
+}
+static int g_pipe_override = -1;                       // la3d_set_pipeline_images (tests, tuning)
+
+static int pipe_get(Pipe** out) {
+  int dev = 0;
+  LA3D_CUDA(cudaGetDevice(&dev));
+  LA3D_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  Pipe& p = g_pipes[dev];
+  if (!p.ready) {
+    int lo = 0, hi = 0;
+    LA3D_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // hi = numerically lowest = greatest priority
+    for (int k = 0; k < 2; ++k) {
+      LA3D_CUDA(cudaStreamCreateWithPriority(&p.side[k], cudaStreamNonBlocking, hi));
+      LA3D_CUDA(cudaEventCreateWithFlags(&p.done[k], cudaEventDisableTiming));
+    }
+    for (int k = 0; k < kMaxParts; ++k) LA3D_CUDA(cudaEventCreateWithFlags(&p.scanned[k], cudaEventDisableTiming));
+    p.ready = true;
+  }
+  *out = &p;
+  return LA3D_OK;
+}
+
+static PrepView prep_part(const PrepView& pv, int b0, int I) {
+  PrepView v = pv;
+  v.cams += b0;
+  v.Rg += (size_t)b0 * I * 9;
+  v.state += (size_t)b0 * kMtN;
+  v.words += (size_t)b0 * pv.nblk * kMtN;
+  return v;
+}
+
+// `produce(b0, Bp, prep_args)` launches the pass that turns images [b0, b0 + Bp) into bit planes + quarter counts
+// (with the preparation CTAs of those images in its grid) on the caller's stream.
+template <typename Produce>
+static int run_step(Produce&& produce, const float* depth, const double* K, const double* ground, int B, int I, int H,
+                    int W, int method, int yaw_steps, uint32_t seed0, const Workspace& w, RecordSink sink,
+                    cudaStream_t stream) {
+  const PrepView pv = prep_view(w.prep, B, I, prep_blocks(I));
+  const int chunks = (int)la3d_chunks_per_plane(H, W);
+  const int per = g_pipe_override >= 0 ? g_pipe_override : pipe_images();
+  int parts = per > 0 ? (B + per - 1) / per : 1;
+  if (parts > kMaxParts) parts = kMaxParts;
+  if (parts <= 1) {
+    const PrepArgs pa{K, ground, B, I, seed0, pv};
+    int rc = produce(0, B, pa);
+    if (rc) return rc;
+    rc = launch_sample(w.chunk_counts, pv, B, I, chunks, w.counts, w.ranks, stream, pdl_enabled());
+    if (rc) return rc;
+    return fit_scanned_sink(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, sink, stream,
+                            pdl_enabled());
+  }
+  Pipe* pipe = nullptr;
+  if (int rc = pipe_get(&pipe)) return rc;
+  std::lock_guard<std::mutex> lock(pipe->mu);             // one enqueue sequence at a time per device
+  sink.total_ctas = (uint32_t)B * (uint32_t)I;            // the release fires after the last CTA of the last part
+  const int step = (B + parts - 1) / parts;
+  bool used[2] = {false, false};
+  for (int p = 0, b0 = 0; b0 < B; ++p, b0 += step) {
+    const int Bp = b0 + step <= B ? step : B - b0;
+    const PrepArgs pa{K + (size_t)b0 * 9, ground ? ground + (size_t)b0 * I * 3 : nullptr, Bp, I, seed0 + (uint32_t)b0,
+                      prep_part(pv, b0, I)};
+    int rc = produce(b0, Bp, pa);
+    if (rc) return rc;
+    cudaStream_t side = pipe->side[p & 1];
+    LA3D_CUDA(cudaEventRecord(pipe->scanned[p], stream));
+    LA3D_CUDA(cudaStreamWaitEvent(side, pipe->scanned[p], 0));
+    rc = launch_sample(w.chunk_counts, pv, Bp, I, chunks, w.counts, w.ranks, side, false, b0);
+    if (rc) return rc;
+    rc = fit_scanned_sink(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, sink, side, false,
+                          b0, Bp);
+    if (rc) return rc;
+    used[p & 1] = true;
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (!used[k]) continue;
+    LA3D_CUDA(cudaEventRecord(pipe->done[k], pipe->side[k]));
+    LA3D_CUDA(cudaStreamWaitEvent(stream, pipe->done[k], 0));
+  }
+  return LA3D_OK;
+}
+
 static int fit_boxes_sink(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
                           int H, int W, int mask_is_01, int method, int yaw_steps, uint32_t seed,
                           uint32_t image_offset, void* workspace, size_t workspace_bytes, const RecordSink& sink,
@@ -133,18 +240,16 @@ static int fit_boxes_sink(const float* depth, const uint8_t* masks, const double
     set_error("la3d_fit_boxes: workspace of %zu bytes, %zu needed", workspace_bytes, w.bytes);
     return LA3D_ENOMEM;
   }
-  // one launch: the scan CTAs plus B CTAs that prepare the batch (MT19937 words, cameras, ground
-  // rotations) under it
   LA3D_REQUIRE(I <= 8192, "at most 8192 instances per image");
-  const PrepView pv = prep_view(w.prep, B, I, prep_blocks(I));
-  const PrepArgs pa{K, ground, B, I, seed + image_offset, pv};
-  int rc = launch_mask_scan(masks, B * I, H, W, mask_is_01, w.bits, w.chunk_counts, &pa, static_cast<cudaStream_t>(stream));
-  if (rc) return rc;
-  rc = launch_sample(w.chunk_counts, pv, B, I, (int)la3d_chunks_per_plane(H, W), w.counts, w.ranks,
-                     static_cast<cudaStream_t>(stream), pdl_enabled());
-  if (rc) return rc;
-  return fit_scanned_sink(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, sink,
-                          static_cast<cudaStream_t>(stream), pdl_enabled());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t HW = (size_t)H * W, words = la3d_words_per_plane(H, W), chunks = la3d_chunks_per_plane(H, W);
+  // one launch per part: the scan CTAs plus the CTAs that prepare the part's images (MT19937 words, cameras,
+  // ground rotations) under it
+  auto produce = [&](int b0, int Bp, const PrepArgs& pa) {
+    const size_t p0 = (size_t)b0 * I;
+    return launch_mask_scan(masks + p0 * HW, Bp * I, H, W, mask_is_01, w.bits + p0 * words, w.chunk_counts + p0 * chunks, &pa, s);
+  };
+  return run_step(produce, depth, K, ground, B, I, H, W, method, yaw_steps, seed + image_offset, w, sink, s);
 }
 
 // Cross-GPU flag operations over peer memory (the fit kernels do both halves themselves, sink.cuh; these
@@ -177,6 +282,7 @@ static int peer_sync(uint32_t* const* flags, int rank, int world, uint32_t epoch
 }
 }  // namespace la3d
 
+extern "C" void la3d_set_pipeline_images(int images_per_part) { la3d::g_pipe_override = images_per_part; }
 extern "C" void la3d_set_peer_timeout_ms(long long ms) { la3d::g_peer_timeout_ms = ms > 0 ? ms : 120000; }
 
 extern "C" int la3d_fit_boxes(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B,
@@ -262,15 +368,16 @@ static int fit_boxes_rle_sink(const float* depth, const uint32_t* run_counts, co
     set_error("la3d_fit_boxes_rle: workspace of %zu bytes, %zu needed", workspace_bytes, w.bytes);
     return LA3D_ENOMEM;
   }
-  // one launch: a CTA per plane decodes its runs into bits + quarter counts, plus the CTAs that prepare the batch
-  const PrepView pv = prep_view(w.prep, B, I, prep_blocks(I));
-  const PrepArgs pa{K, ground, B, I, seed + image_offset, pv};
+  // one launch per part: a CTA per plane decodes its runs into bits + quarter counts, plus the CTAs that prepare
+  // the part's images
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int rc = launch_rle_decode(run_counts, run_offsets, B * I, H, W, max_runs, ends_ws, w.bits, w.chunk_counts, rle_status, &pa, s);
-  if (rc) return rc;
-  rc = launch_sample(w.chunk_counts, pv, B, I, (int)la3d_chunks_per_plane(H, W), w.counts, w.ranks, s, false);
-  if (rc) return rc;
-  return fit_scanned_sink(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, sink, s, false);
+  const size_t words = la3d_words_per_plane(H, W), chunks = la3d_chunks_per_plane(H, W);
+  auto produce = [&](int b0, int Bp, const PrepArgs& pa) {
+    const size_t p0 = (size_t)b0 * I;
+    return launch_rle_decode(run_counts, run_offsets + p0, Bp * I, H, W, max_runs, ends_ws, w.bits + p0 * words,
+                             w.chunk_counts + p0 * chunks, rle_status + p0, &pa, s);
+  };
+  return run_step(produce, depth, K, ground, B, I, H, W, method, yaw_steps, seed + image_offset, w, sink, s);
 }
 }  // namespace la3d
 

@@ -233,7 +233,8 @@ struct PrepView {
 };
 PrepView prep_view(void* base, int B, int I, int nblk);
 int prep_blocks(int I);
+// images [b0, b0 + B) of the batch the pointers describe
 int launch_sample(const uint32_t* chunk_counts, const PrepView& pv, int B, int I, int chunks, int32_t* counts,
-                  int32_t* ranks, cudaStream_t s, bool pdl = false);
+                  int32_t* ranks, cudaStream_t s, bool pdl = false, int b0 = 0);
 
 }  // namespace la3d

@@ -53,6 +53,7 @@ struct FitArgs {
   const double* K;        // [images or boxes][9] intrinsics; may be null for explicit points
   const double* ground;   // [boxes][3] or null
   int method, yaw_steps, n_areas;
+  int box0;               // first box of this launch (a step may be cut into several launches over one set of buffers)
   RecordSink sink;        // one local buffer, or the gathered buffers of all ranks (peer memory); sink.cuh
 };
 
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
     sm.hull = sm.cand + kMaxPts;
   }
 
-  const int box = blockIdx.x;
+  const int box = blockIdx.x + a.box0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int img = kScanned ? box / a.I : box;
 
@@ -623,21 +624,25 @@ int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s, bool pdl = 
 }  // namespace la3d
 
 namespace la3d {
+// The boxes of images [b0, b0 + Bp) of a batch of B; every pointer is the whole batch's.
 int fit_scanned_sink(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
                      const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
-                     const RecordSink& sink, cudaStream_t stream, bool pdl) {
+                     const RecordSink& sink, cudaStream_t stream, bool pdl, int b0, int Bp) {
   LA3D_REQUIRE(depth && prep && bits && chunk_counts && ranks, "null pointer");
   LA3D_REQUIRE(B > 0 && I > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
   LA3D_REQUIRE(method != LA3D_METHOD_SWEEP || (yaw_steps > 0 && yaw_steps <= 16384), "sweep needs 1 <= yaw_steps <= 16384");
+  if (Bp < 0) Bp = B - b0;
+  LA3D_REQUIRE(b0 >= 0 && Bp > 0 && b0 + Bp <= B, "bad image range");
   const PrepView pv = prep_view(const_cast<void*>(prep), B, I, prep_blocks(I));
   FitArgs a{};
   a.depth = depth; a.bits = bits; a.chunk_counts = chunk_counts; a.ranks = ranks;
   a.cams = pv.cams; a.Rg_pre = pv.Rg;
   a.I = I; a.HW = H * W; a.W = W; a.chunks = (int)la3d_chunks_per_plane(H, W);
   a.method = method; a.yaw_steps = yaw_steps;
+  a.box0 = b0 * I;
   a.sink = sink;
-  return launch_fit(true, a, B * I, stream, pdl);
+  return launch_fit(true, a, Bp * I, stream, pdl);
 }
 }  // namespace la3d
 

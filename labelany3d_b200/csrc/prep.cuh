@@ -156,7 +156,7 @@ int launch_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes
 struct RecordSink;
 int fit_scanned_sink(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
                      const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps,
-                     const RecordSink& sink, cudaStream_t stream, bool pdl = false);
+                     const RecordSink& sink, cudaStream_t stream, bool pdl = false, int b0 = 0, int Bp = -1);
 int fit_all_sink(const float* depth, const void* prep, const uint32_t* bits, int B, int I, int H, int W, int method,
                  int yaw_steps, const RecordSink& sink, cudaStream_t stream);
 

@@ -46,14 +46,14 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepArgs pa) {
 
 __global__ void __launch_bounds__(kThreads) sample_kernel(const uint32_t* __restrict__ chunk_counts, int I, int chunks,
                                                           PrepView pv, int seg_cap, int32_t* __restrict__ counts,
-                                                          int32_t* __restrict__ ranks) {
+                                                          int32_t* __restrict__ ranks, int b0) {
   __shared__ uint32_t mt[kMtN];               // generator state, only if the pre-generated words run out
   __shared__ int wtot[kWarps], end_pos;
   extern __shared__ __align__(16) uint32_t dyn[];
   uint32_t* seg = dyn;                        // [seg_cap] staged words
   uint32_t* n_of = dyn + seg_cap;             // [I] set pixels per instance
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x + b0;
   const int nwords = pv.nblk * kMtN;          // pre-generated words of this image
   const uint32_t* words = pv.words + (size_t)b * nwords;
 
@@ -207,13 +207,13 @@ PrepView prep_view(void* base, int B, int I, int nblk) {
 int prep_blocks(int I) { return auto_blocks(I); }
 
 int launch_sample(const uint32_t* chunk_counts, const PrepView& pv, int B, int I, int chunks, int32_t* counts,
-                  int32_t* ranks, cudaStream_t s, bool pdl) {
+                  int32_t* ranks, cudaStream_t s, bool pdl, int b0) {
   const int seg_cap = (pv.nblk < kSegBlocksMax ? pv.nblk : kSegBlocksMax) * kMtN;
   const size_t dyn = ((size_t)seg_cap + I) * 4;
   if (dyn > 48 * 1024)
     LA3D_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   LA3D_CUDA(launch_pdl(sample_kernel, dim3((unsigned)B), dim3(kThreads), dyn, s, pdl, chunk_counts, I, chunks, pv, seg_cap,
-                       counts, ranks));
+                       counts, ranks, b0));
   return LA3D_OK;
 }
 

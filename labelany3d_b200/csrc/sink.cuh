@@ -24,6 +24,7 @@ struct RecordSink {
   int32_t* status;                    // sticky error word (host-visible), set to 1 before a timeout trap
   unsigned long long timeout_ns;
   uint32_t epoch;
+  uint32_t total_ctas;                // CTAs (over all launches of the step) that count towards the release; 0 = this grid
   int n_out, rank, rec_f64;
 };
 
@@ -111,7 +112,7 @@ __device__ __forceinline__ void sink_release(const RecordSink& s) {
   if (threadIdx.x == 0) {
     __threadfence_system();
     const uint32_t done = atomicAdd(s.counter, 1u);
-    if (done == gridDim.x * gridDim.y - 1u) {
+    if (done == (s.total_ctas ? s.total_ctas : gridDim.x) - 1u) {
       *s.counter = 0u;                               // ready for the next launch
       __threadfence_system();                        // the other CTAs' fenced stores are ordered before the flags
       for (int p = 0; p < s.n_out; ++p) st_release_sys(s.flags[p] + s.rank, s.epoch);

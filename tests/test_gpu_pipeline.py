@@ -1,0 +1,49 @@
+"""The step cut into parts (scan of part p+1 under the sampler + fit of part p on internal high-priority
+streams): records must not depend on the split, for byte masks and run-length input, and the call must
+remain capturable into a CUDA graph."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def lib():
+    from labelany3d_b200 import _lib
+    lib = _lib.load()
+    yield lib
+    lib.la3d_set_pipeline_images(-1)
+
+
+@pytest.mark.parametrize("method,steps", [("pca", 0), ("sweep", 36), ("convex_hull", 0)])
+def test_records_do_not_depend_on_the_split(lib, method, steps):
+    from labelany3d_b200 import coco_rle, ops, synth
+    B, I, H, W = 11, 3, 96, 160
+    depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=21, device="cuda", area=(0.05, 0.3))
+    lib.la3d_set_pipeline_images(0)
+    want = ops.fit_boxes(depth, K, masks, ground, method, steps, seed=7)
+    counts, offsets, max_runs = coco_rle.runs_from_masks_device(masks.reshape(-1, H, W))
+    for per in (1, 2, 4, 5, 11, 64):                      # 11 parts ... 1 part; uneven last parts
+        lib.la3d_set_pipeline_images(per)
+        for _ in range(3):                                 # back-to-back calls reuse the side streams and events
+            got = ops.fit_boxes(depth, K, masks, ground, method, steps, seed=7)
+        assert torch.equal(got.view(torch.int64), want.view(torch.int64)), per
+        rle = ops.RleBoxFitter(B, I, H, W, counts.numel(), max_runs)(depth, K, counts, offsets, ground, method, steps, seed=7)
+        assert torch.equal(rle.view(torch.int64), want.view(torch.int64)), per
+
+
+def test_split_step_in_a_cuda_graph(lib):
+    from labelany3d_b200 import ops, synth
+    B, I, H, W = 8, 2, 64, 96
+    depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=22, device="cuda", area=(0.05, 0.3))
+    lib.la3d_set_pipeline_images(0)
+    want = ops.fit_boxes(depth, K, masks, ground, "sweep", 12, seed=3)
+    lib.la3d_set_pipeline_images(3)
+    fitter = ops.BoxFitter(B, I, H, W)
+    replay, rec = fitter.capture(depth, K, masks, ground, "sweep", 12, seed=3)
+    rec.fill_(0)
+    replay()
+    replay()
+    torch.cuda.synchronize()
+    assert torch.equal(rec.view(torch.int64), want.view(torch.int64))
