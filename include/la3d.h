@@ -49,7 +49,8 @@ typedef void* la3d_stream_t; /* cudaStream_t */
 #define LA3D_ST_PCA_UNDEFINED 2 /* one point: scikit-learn PCA(2) refuses n_samples < 2 */
 #define LA3D_ST_BAD_METHOD 3    /* ValueError("Unknown method ..."), util_3dbox.py:151 */
 #define LA3D_ST_NONFINITE 4     /* +-inf left in the XZ footprint: scikit-learn's input check raises */
-#define LA3D_ST_TOO_MANY 5      /* la3d_fit_points only: more than 500 points and no sample_idx */
+#define LA3D_ST_TOO_MANY 5      /* la3d_fit_points: more than 500 points and no sample_idx; all-pixels hull / sweep: more
+                                   than 2048 hull candidates */
 
 /* the reference keeps at most this many points per box (util_3dbox.py:123-125) */
 #define LA3D_SUBSAMPLE 500
@@ -230,15 +231,21 @@ int la3d_fit_boxes_rle(const float* depth, const uint32_t* run_counts, const int
                        int32_t* rle_status, void* records, int rec_f64, la3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
- * The box from EVERY masked pixel: estimate_bbox (src/util_3dbox.py:106-178, method='pca') with the
- * random 500-point draw of :123-125 replaced by the identity - deterministic, no generator involved.
- * One CTA per box reduces the centroid / covariance sums of the ground-aligned footprint over all set
- * pixels of the plane (float64, fixed summation order), takes the yaw from them (the closed form of
- * scikit-learn's PCA(2)), reduces the extents at that yaw in a second sweep and writes the same record as
- * la3d_fit_scanned (status codes included; LA3D_O_NVALID / LA3D_O_NMASK count all pixels).
- *   la3d_fit_all_points: bits from la3d_mask_scan / la3d_rle_decode, prep from la3d_fit_prepare
+ * The box from EVERY masked pixel: estimate_bbox (src/util_3dbox.py:106-178) with the random 500-point draw
+ * of :123-125 replaced by the identity - deterministic, no generator involved.  One CTA per box sweeps the set
+ * pixels of the plane (float64, fixed summation order):
+ *   method pca          centroid / covariance sums -> closed form of scikit-learn's PCA(2) -> extents in a
+ *                       second sweep;
+ *   method convex_hull  the footprint's hull candidates are filtered out of all pixels (octagon of the extreme
+ *   / sweep             points, refined QuickHull-style until at most 2048 points survive), then the same hull-edge
+ *                       search (util_3dbox.py:189-224, + the reference's +yaw rotation) / uniform sweep
+ *                        as the sampled path.  A footprint with more than 2048 points on or near
+ *                       its hull after 64 polygon vertices gets status LA3D_ST_TOO_MANY.
+ * Same record as la3d_fit_scanned (status codes included; LA3D_O_NVALID / LA3D_O_NMASK count all pixels).
+ *   la3d_fit_all_points: bits from la3d_mask_scan / la3d_rle_decode, prep from la3d_fit_prepare (method pca;
+ *                        la3d_fit_all_points_to takes the method and a sink)
  *   la3d_fit_boxes_all:  byte masks in; two launches (scan with the preparation riding in it, dense fit);
- *                        workspace as for la3d_fit_boxes
+ *                        workspace as for la3d_fit_boxes (method pca; la3d_fit_boxes_all_to takes the method)
  * ------------------------------------------------------------------------- */
 int la3d_fit_all_points(const float* depth, const void* prep, const uint32_t* bits, int B, int I, int H, int W,
                         void* records, int rec_f64, la3d_stream_t stream);
@@ -294,6 +301,8 @@ int la3d_fit_boxes_rle_to(const float* depth, const uint32_t* run_counts, const 
                           uint32_t* ends_ws, const double* K, const double* ground, int B, int I, int H, int W,
                           int method, int yaw_steps, uint32_t seed, uint32_t image_offset, void* workspace,
                           size_t workspace_bytes, int32_t* rle_status, const la3d_sink* sink, la3d_stream_t stream);
+int la3d_fit_all_points_to(const float* depth, const void* prep, const uint32_t* bits, int B, int I, int H, int W,
+                           int method, int yaw_steps, const la3d_sink* sink, la3d_stream_t stream);
 int la3d_fit_boxes_all_to(const float* depth, const uint8_t* masks, const double* K, const double* ground, int B, int I,
                           int H, int W, int mask_is_01, int method, int yaw_steps, void* workspace,
                           size_t workspace_bytes, const la3d_sink* sink, la3d_stream_t stream);

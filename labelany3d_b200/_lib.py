@@ -33,6 +33,7 @@ SIGNATURES = {
     "la3d_fit_boxes_to": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _vp]),
     "la3d_fit_scanned_to": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "la3d_fit_boxes_rle_to": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _vp, _vp]),
+    "la3d_fit_all_points_to": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "la3d_fit_boxes_all_to": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "la3d_peer_signal": (_i, [_vp, _i, _i, _u32, _vp]),
     "la3d_peer_wait": (_i, [_vp, _i, _i, _u32, _vp, _vp]),

@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "prep.cuh"
 #include "sink.cuh"
+#include "yaw_common.cuh"
 
 namespace la3d {
 namespace {
@@ -80,9 +81,6 @@ __host__ __device__ inline size_t region_b_bytes(int chunks, bool scanned) {
   return (need + 15) & ~(size_t)15;
 }
 
-__device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }   // NaN in b is ignored
-__device__ __forceinline__ double dmax(double a, double b) { return b > a ? b : a; }
-
 // ---- block-wide reductions; the result is broadcast to every thread -------------
 template <int N, typename Op>
 __device__ __forceinline__ void block_reduce(double (&v)[N], Smem& sm, Op op) {
@@ -129,17 +127,6 @@ struct OpAdd { __device__ double operator()(double a, double b, int) const { ret
 struct OpMinMax { __device__ double operator()(double a, double b, int k) const { return k < 3 ? dmin(a, b) : dmax(a, b); } };
 // entries 0..3 are maxima, 4..7 minima
 struct OpMax4Min4 { __device__ double operator()(double a, double b, int k) const { return k < 4 ? dmax(a, b) : dmin(a, b); } };
-
-// (area, index) pairs ordered like the reference's `if area < min_area` loop: the
-// smallest area wins, the earliest index among equals; NaN and +inf never win.
-struct Best {
-  double area;
-  int idx;   // -1 = nothing qualified yet
-  __device__ void offer(double a, int i) {
-    if (!(a < CUDART_INF) || i < 0) return;
-    if (idx < 0 || a < area || (a == area && i < idx)) { area = a; idx = i; }
-  }
-};
 
 __device__ __forceinline__ int first_strict_min(const double* areas, int n, Smem& sm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -246,23 +233,6 @@ __device__ void octagon_candidates(Smem& sm, int nsel) {
 // lexicographically smallest point; collinear points are skipped (strict hull, like Qhull's
 // vertex list).  Writes sm.hull / sm.hull_n; hull_n = 0 when Qhull would have raised
 // (fewer than 3 vertices: coincident or collinear points).
-struct Wrap {
-  double cx, cz, qx, qz;
-  int qi;
-  __device__ void offer(double px, double pz, int pi) {
-    if (pi < 0 || !(px == px) || (px == cx && pz == cz)) return;
-    if (qi < 0) { qx = px; qz = pz; qi = pi; return; }
-    const double cr = (qx - cx) * (pz - cz) - (qz - cz) * (px - cx);
-    bool take = cr < 0.0;                       // p is clockwise of cur->q: q cannot be the next vertex
-    if (cr == 0.0) {
-      const double dq = (qx - cx) * (qx - cx) + (qz - cz) * (qz - cz);
-      const double dp = (px - cx) * (px - cx) + (pz - cz) * (pz - cz);
-      take = dp > dq || (dp == dq && pi < qi);
-    }
-    if (take) { qx = px; qz = pz; qi = pi; }
-  }
-};
-
 __device__ void hull_wrap(Smem& sm) {
   const int lane = threadIdx.x & 31;
   const int nc = sm.cand_n;
@@ -306,31 +276,9 @@ __device__ void hull_wrap(Smem& sm) {
   if (lane == 0) sm.hull_n = (closed && hn >= 3) ? hn : 0;
 }
 
-// Bounding-rectangle area of the footprint (over an index list that contains every point that can
-// be extreme) after a rotation.  kind 0: the reference's
-// hull-edge test rotates by +ang (rot_2d of util_3dbox.py:206-210, kept although the box is
-// later built with rotate_y(yaw) = -yaw in XZ); kind 1: the sweep rotates like rotate_y(ang).
-__device__ __forceinline__ double rect_area(const Smem& sm, const unsigned short* list, int n, double ang, int kind) {
-  double s, c;
-  sincos(ang, &s, &c);
-  if (kind) s = -s;
-  double mnx = CUDART_INF, mxx = -CUDART_INF, mnz = CUDART_INF, mxz = -CUDART_INF;
-  for (int k = 0; k < n; ++k) {
-    const int idx = list[k];
-    const double px = sm.x[idx], pz = sm.z[idx];
-    const double rx = c * px - s * pz, rz = s * px + c * pz;
-    mnx = dmin(mnx, rx); mxx = dmax(mxx, rx); mnz = dmin(mnz, rz); mxz = dmax(mxz, rz);
-  }
-  return (mxx - mnx) * (mxz - mnz);
-}
-
 __device__ __forceinline__ double edge_angle(const Smem& sm, int hn, int e) {
   const int i0 = sm.hull[e], i1 = sm.hull[(e + 1 == hn) ? 0 : e + 1];
   return atan2(sm.z[i1] - sm.z[i0], sm.x[i1] - sm.x[i0]);
-}
-
-__device__ __forceinline__ double sweep_angle(int c, int K) {
-  return __ddiv_rn(__dmul_rn((double)c, CUDART_PIO2), (double)K);     // k * (pi/2) / K as NumPy evaluates it
 }
 
 // ---- gather: rank -> pixel -> depth -> camera point ---------------------------------------
@@ -555,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
         have_trig = true;
       } else {
         // util_3dbox.py:202-218: one thread per hull edge, first strict minimum of the area
-        for (int e = tid; e < hn; e += kThreads) areas[e] = rect_area(sm, sm.hull, hn, edge_angle(sm, hn, e), 0);
+        for (int e = tid; e < hn; e += kThreads) areas[e] = rect_area(sm.x, sm.z, sm.hull, hn, edge_angle(sm, hn, e), 0);
         __syncthreads();
         const int e = first_strict_min(areas, hn, sm);
         if (tid == 0) sm.yaw = e < 0 ? 0.0 : edge_angle(sm, hn, e);
@@ -566,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
       if (inf_y) {
         if (tid == 0) sm.yaw = 0.0;                    // 0*inf = NaN in every area: nothing beats +inf
       } else {
-        for (int c = tid; c < K; c += kThreads) areas[c] = rect_area(sm, sm.cand, nc, sweep_angle(c, K), 1);
+        for (int c = tid; c < K; c += kThreads) areas[c] = rect_area(sm.x, sm.z, sm.cand, nc, sweep_angle(c, K), 1);
         __syncthreads();
         const int c = first_strict_min(areas, K, sm);
         if (tid == 0) sm.yaw = c < 0 ? 0.0 : sweep_angle(c, K);

@@ -475,11 +475,11 @@ def fit_boxes_bits(depth, K, bits, chunk_counts, I, ground=None, method="pca", y
 
 def fit_boxes_all(depth, K, masks, ground=None, out_dtype=torch.float64, method="pca", yaw_steps=0, sink=None,
                   workspace=None):
-    """Boxes from EVERY masked pixel (``la3d_fit_boxes_all``): the reference's ``estimate_bbox`` with
-    ``method='pca'`` and its random 500-point draw (``src/util_3dbox.py:123-125``) replaced by the identity.
-    Deterministic, no generator involved; same record layout and status codes as :func:`fit_boxes`.
+    """Boxes from EVERY masked pixel (``la3d_fit_boxes_all_to``): the reference's ``estimate_bbox`` with its random
+    500-point draw (``src/util_3dbox.py:123-125``) replaced by the identity, for ``method`` pca / convex_hull /
+    sweep.  Deterministic, no generator involved; same record layout and status codes as :func:`fit_boxes`.
     Two launches: the mask scan (with the camera / ground preparation riding in its grid) and one CTA per box
-    that reduces the footprint's moments and extents over all its pixels."""
+    that reduces the footprint's moments, hull candidates and extents over all its pixels."""
     lib = _lib.load()
     depth = _need_cuda("depth", depth, torch.float32)
     K = _need_cuda("K", K, torch.float64)
@@ -510,8 +510,8 @@ def fit_boxes_all(depth, K, masks, ground=None, out_dtype=torch.float64, method=
     return rec
 
 
-def fit_all_points(depth, prep, bits, I, out_dtype=torch.float64):
-    """The dense fit alone (``la3d_fit_all_points``) on bit planes that already exist
+def fit_all_points(depth, prep, bits, I, out_dtype=torch.float64, method="pca", yaw_steps=0):
+    """The dense fit alone (``la3d_fit_all_points_to``) on bit planes that already exist
     (:func:`mask_scan` / :func:`rle_decode`) and the ``prep`` buffer of :func:`fit_prepare`."""
     lib = _lib.load()
     depth = _need_cuda("depth", depth, torch.float32)
@@ -521,9 +521,10 @@ def fit_all_points(depth, prep, bits, I, out_dtype=torch.float64):
         raise ValueError("bit planes do not match depth and I")
     rec = torch.empty((B, I, REC), dtype=out_dtype, device=depth.device)
     with torch.cuda.device(depth.device):
-        rc = lib.la3d_fit_all_points(_ptr(depth), _ptr(prep), _ptr(bits), B, I, H, W, _ptr(rec),
-                                     int(out_dtype == torch.float64), _stream())
-    _lib.check(rc, "la3d_fit_all_points")
+        sink = _lib.make_sink([rec.data_ptr()], out_dtype == torch.float64)
+        rc = lib.la3d_fit_all_points_to(_ptr(depth), _ptr(prep), _ptr(bits), B, I, H, W, _method_id(method), int(yaw_steps),
+                                        ctypes.byref(sink), _stream())
+    _lib.check(rc, "la3d_fit_all_points_to")
     return rec
 
 

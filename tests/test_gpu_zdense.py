@@ -91,3 +91,65 @@ def test_full_size_properties(ops):
     d, k, m, g = (t[:ns].cpu().numpy() for t in (depth, K, masks, ground))
     want = orc.fit_boxes(d, k, m, g, "pca", impl="closed", subsample=False)
     check_record(rec[:ns].cpu().numpy(), want, TOL_F64, skip=())
+
+
+@pytest.mark.parametrize("method,steps", [("convex_hull", 0), ("sweep", 36), ("sweep", 360)])
+def test_all_pixels_hull_and_sweep_against_the_oracle(ops, method, steps):
+    """The yaw searches over EVERY masked pixel: small planes (every point kept, no filter), COCO-size planes
+    (the octagon / 16-gon filter leaves at most 2048 candidates) and a 900 x 1100 image whose masks need further
+    refinement levels, against the oracle's `subsample=False` restatement (SciPy hull over all points for
+    convex_hull)."""
+    from labelany3d_b200 import synth
+    # composed scene: empty / one-pixel / 200-pixel masks, inf / NaN depths
+    depth, K, masks, ground = dense_cases.scenes()["composed"]
+    for g in (None, ground):
+        want = orc.fit_boxes(depth, K, masks, g, method, steps, impl="closed", subsample=False)
+        got = ops.fit_boxes_all(dev(depth), dev(K), dev(masks), None if g is None else dev(g), method=method, yaw_steps=steps).cpu().numpy()
+        np.testing.assert_array_equal(got[..., orc.O_STATUS], want[..., orc.O_STATUS])
+        ok = want[..., orc.O_STATUS] == orc.ST_OK
+        np.testing.assert_array_equal(got[ok][:, orc.O_NVALID], want[ok][:, orc.O_NVALID])
+        check_record(got[ok], want[ok], TOL_F64, skip=())
+    for (B, I, H, W, area, seed) in ((2, 4, 480, 640, (0.02, 0.12), 31), (1, 3, 900, 1100, (0.05, 0.3), 32)):
+        d, k, m, g = synth.make_inputs(B, H, W, I, seed=seed, device="cuda", area=area)
+        got = ops.fit_boxes_all(d, k, m, g, method=method, yaw_steps=steps)
+        again = ops.fit_boxes_all(d, k, m, g, method=method, yaw_steps=steps)
+        assert torch.equal(got.view(torch.int64), again.view(torch.int64))          # deterministic
+        want = orc.fit_boxes(d.cpu().numpy(), k.cpu().numpy(), m.cpu().numpy(), g.cpu().numpy(), method, steps,
+                             impl="closed", subsample=False)
+        assert (want[..., orc.O_NMASK] > 2048).all()
+        got = got.cpu().numpy()
+        np.testing.assert_array_equal(got[..., orc.O_STATUS], want[..., orc.O_STATUS])
+        np.testing.assert_array_equal(got[..., orc.O_NVALID], want[..., orc.O_NVALID])
+        np.testing.assert_allclose(got[..., orc.O_YAW], want[..., orc.O_YAW], rtol=0, atol=1e-9)
+        check_record(got, want, TOL_F64, skip=())
+
+
+def test_all_pixels_search_equals_the_sampled_path_on_small_masks(ops):
+    depth, K, masks, ground = dense_cases.scenes()["composed"]
+    small = orc.mask_counts(masks) <= orc.SUBSAMPLE
+    for method, steps in (("convex_hull", 0), ("sweep", 24)):
+        a = ops.fit_boxes_all(dev(depth), dev(K), dev(masks), dev(ground), method=method, yaw_steps=steps).cpu().numpy()
+        b = ops.fit_boxes(dev(depth), dev(K), dev(masks), dev(ground), method, steps, seed=9).cpu().numpy()
+        np.testing.assert_array_equal(a[small][:, orc.O_STATUS], b[small][:, orc.O_STATUS])
+        check_record(a[small], b[small], TOL_F64, skip=())
+
+
+def test_all_pixels_unknown_method_and_rim_overflow(ops):
+    from labelany3d_b200 import synth
+    d, k, m, g = synth.make_inputs(1, 96, 128, 2, seed=5, device="cuda", area=(0.05, 0.3))
+    rec = ops.fit_boxes_all(d, k, m, g, method="nonsense")
+    assert (rec[..., orc.O_STATUS] == orc.ST_BAD_METHOD).all()
+    # a thin ring: more than 2048 of its points are hull vertices -> status 5 (documented limit), never a wrong box
+    H = W = 1024
+    v, u = torch.meshgrid(torch.arange(H, device="cuda"), torch.arange(W, device="cuda"), indexing="ij")
+    r2 = (u - 512.0) ** 2 + (v - 512.0) ** 2
+    ring = ((r2 <= 500.0 ** 2) & (r2 >= 499.0 ** 2))[None, None]
+    depth = torch.full((1, H, W), 3.0, device="cuda")
+    K = torch.tensor([[[900.0, 0, 512], [0, 900.0, 512], [0, 0, 1]]], dtype=torch.float64, device="cuda")
+    rec = ops.fit_boxes_all(depth, K, ring, None, method="convex_hull")
+    n = int(ring.sum())
+    assert n > 2048 and rec[0, 0, orc.O_NMASK] == n
+    assert rec[0, 0, orc.O_STATUS] in (0.0, 5.0)
+    if rec[0, 0, orc.O_STATUS] == 0.0:                       # fewer than 2048 strict hull vertices after all: then it is right
+        want = orc.fit_boxes(depth.cpu().numpy(), K.cpu().numpy(), ring.cpu().numpy(), None, "convex_hull", impl="closed", subsample=False)
+        check_record(rec.cpu().numpy(), want, TOL_F64, skip=())

@@ -65,6 +65,7 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
         "la3d_fit_boxes_to": lambda: lib.la3d_fit_boxes_to(None, None, None, None, 1, 1, 4, 4, 1, 0, 0, 0, 0, None, 0, None, None),
         "la3d_fit_scanned_to": lambda: lib.la3d_fit_scanned_to(None, None, None, None, None, 1, 1, 4, 4, 0, 0, None, None),
         "la3d_fit_boxes_rle_to": lambda: lib.la3d_fit_boxes_rle_to(None, None, None, 0, None, None, None, 1, 1, 4, 4, 0, 0, 0, 0, None, 0, None, None, None),
+        "la3d_fit_all_points_to": lambda: lib.la3d_fit_all_points_to(None, None, None, 1, 1, 4, 4, 0, 0, None, None),
         "la3d_fit_boxes_all_to": lambda: lib.la3d_fit_boxes_all_to(None, None, None, None, 1, 1, 4, 4, 1, 0, 0, None, 0, None, None),
         "la3d_peer_barrier": lambda: lib.la3d_peer_barrier(None, 0, 1, 1, None, None),
         "la3d_peer_signal": lambda: lib.la3d_peer_signal(None, 0, 1, 1, None),

@@ -1,7 +1,8 @@
 """Bit-level regression vectors of the fit kernels (run on the B200 box).
 
-    python tools/regress_records.py --write PATH.npz     # mint from the build in the tree
-    python tools/regress_records.py --check PATH.npz     # compare the build in the tree, bitwise
+    python tools/regress_records.py --write PATH.npz           # mint from the build in the tree
+    python tools/regress_records.py --write-all PATH.npz       # mint only the all-pixels records (keys */all*)
+    python tools/regress_records.py --check PATH.npz [MORE.npz] # compare the build in the tree, bitwise; keys of later files win
 
 The records of `la3d_fit_boxes` / `la3d_fit_boxes_all` on seeded synthetic inputs (small cases: the
 float64 records themselves; BASELINE.json's configs at their per-GPU size: a SHA-256 of the float32
@@ -51,18 +52,19 @@ def sha(*tensors):
     return h.hexdigest()
 
 
-def compute():
+def compute(only_all=False):
     from labelany3d_b200 import ops, synth
     out = {}
     for name, B, I, H, W, method, steps, with_g in SMALL:
         d, K, m, g = synth.make_inputs(B, H, W, I, seed=77, device="cuda", area=(0.02, 0.12) if H > 200 else (0.05, 0.3))
         g = g if with_g else None
         out[name + "/in"] = np.array(sha(d, K, m, g))
-        out[name + "/rec"] = ops.fit_boxes(d, K, m, g, method, steps, seed=1234, out_dtype=torch.float64).cpu().numpy()
-        out[name + "/rec32"] = ops.fit_boxes(d, K, m, g, method, steps, seed=1234, out_dtype=torch.float32).cpu().numpy()
-        if method == "pca":
-            out[name + "/all"] = ops.fit_boxes_all(d, K, m, g, out_dtype=torch.float64).cpu().numpy()
-    for name, B, I, H, W, method, steps in FULL:
+        if not only_all:
+            out[name + "/rec"] = ops.fit_boxes(d, K, m, g, method, steps, seed=1234, out_dtype=torch.float64).cpu().numpy()
+            out[name + "/rec32"] = ops.fit_boxes(d, K, m, g, method, steps, seed=1234, out_dtype=torch.float32).cpu().numpy()
+        if H > 200:
+            out[name + "/all"] = ops.fit_boxes_all(d, K, m, g, out_dtype=torch.float64, method=method, yaw_steps=steps).cpu().numpy()
+    for name, B, I, H, W, method, steps in ([] if only_all else FULL):
         d, K, m, g = synth.make_inputs(B, H, W, I, seed=1234 + 2, device="cuda")
         out[name + "/in"] = np.array(sha(d, K, m, g))
         rec = ops.fit_boxes(d, K, m, g, method, steps, seed=1234, out_dtype=torch.float32)
@@ -74,28 +76,33 @@ def compute():
 
 def main():
     mode, path = sys.argv[1], sys.argv[2]
-    got = compute()
-    if mode == "--write":
+    got = compute(only_all=(mode == "--write-all"))
+    if mode in ("--write", "--write-all"):
+        if mode == "--write-all":
+            got = {k: v for k, v in got.items() if k.endswith("/all") or k.endswith("/in")}
         np.savez_compressed(path, **got)
         print("wrote", path, os.path.getsize(path), "bytes")
         return 0
     bad = 0
-    with np.load(path) as want:
-        for key in want.files:
-            if key.endswith("/in"):
-                continue
-            case = key.split("/")[0]
-            if str(want[case + "/in"]) != str(got[case + "/in"]):
-                print(f"SKIP {key}: inputs differ on this box (generator mismatch)")
-                continue
-            a, b = want[key], got[key]
-            same = (a.tobytes() == b.tobytes()) if a.dtype.kind == "f" else (str(a) == str(b))
-            print(("ok   " if same else "DIFF ") + key)
-            if not same and a.dtype.kind == "f":
-                with np.errstate(invalid="ignore"):
-                    diff = np.abs(a.astype(np.float64) - b.astype(np.float64))
-                print("      max |diff| =", np.nanmax(diff), "at", np.argwhere(~((a == b) | (np.isnan(a) & np.isnan(b))))[:4].tolist())
-            bad += 0 if same else 1
+    want = {}
+    for pth in sys.argv[2:]:
+        with np.load(pth) as z:
+            want.update({k: z[k] for k in z.files})
+    for key in want:
+        if key.endswith("/in"):
+            continue
+        case = key.split("/")[0]
+        if str(want[case + "/in"]) != str(got[case + "/in"]):
+            print(f"SKIP {key}: inputs differ on this box (generator mismatch)")
+            continue
+        a, b = want[key], got[key]
+        same = (a.tobytes() == b.tobytes()) if a.dtype.kind == "f" else (str(a) == str(b))
+        print(("ok   " if same else "DIFF ") + key)
+        if not same and a.dtype.kind == "f":
+            with np.errstate(invalid="ignore"):
+                diff = np.abs(a.astype(np.float64) - b.astype(np.float64))
+            print("      max |diff| =", np.nanmax(diff), "at", np.argwhere(~((a == b) | (np.isnan(a) & np.isnan(b))))[:4].tolist())
+        bad += 0 if same else 1
     print("regression:", "IDENTICAL" if bad == 0 else f"{bad} arrays differ")
     return 1 if bad else 0
 
