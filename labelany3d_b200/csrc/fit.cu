@@ -64,7 +64,7 @@ struct Smem {
   double x[kMaxPts], z[kMaxPts];               // ground-aligned footprint; x = NaN marks a dropped row
   double red[kWarps][8];
   double Kinv[9], Kmat[9], Rg[9];
-  double oct[8][2];                            // extreme points of the footprint (octagon, CCW)
+  int oct_idx[8];                              // extreme points of the footprint (octagon, CCW): indices into x / z
   double yaw, cos_yaw, sin_yaw;
   int ired[kWarps][4];
   int cand_n, hull_n;
@@ -192,18 +192,24 @@ __device__ void octagon_candidates(Smem& sm, int nsel) {
   }
   block_reduce(e, sm, OpMax4Min4());
   if (threadIdx.x == 0) sm.cand_n = 0;
-  // any point attaining an extreme serves as that octagon vertex (ties write the same role; either is valid)
+  if (threadIdx.x < 8) sm.oct_idx[threadIdx.x] = 0x7fffffff;
+  __syncthreads();
+  // any point attaining an extreme serves as that octagon vertex; among ties the smallest index is elected, so
+  // that both coordinates come from ONE input point whatever the thread schedule
   for (int k = threadIdx.x; k < nsel; k += kThreads) {
     const double px = sm.x[k], pz = sm.z[k];
     const double f[8] = {px, px + pz, pz, pz - px, px, px + pz, pz, pz - px};
 #pragma unroll
     for (int d = 0; d < 8; ++d)
-      if (f[d] == e[d]) { sm.oct[d][0] = px; sm.oct[d][1] = pz; }
+      if (f[d] == e[d]) atomicMin(&sm.oct_idx[d], k);
   }
   __syncthreads();
   double ox[8], oz[8];
 #pragma unroll
-  for (int d = 0; d < 8; ++d) { ox[d] = sm.oct[d][0]; oz[d] = sm.oct[d][1]; }
+  for (int d = 0; d < 8; ++d) {
+    const int k = min(sm.oct_idx[d], nsel - 1);        // always elected: e[d] is attained by a valid point
+    ox[d] = sm.x[k]; oz[d] = sm.z[k];
+  }
   for (int k0 = 0; k0 < nsel; k0 += kThreads) {
     const int k = k0 + threadIdx.x;
     bool keep = false;
@@ -269,6 +275,10 @@ __device__ void hull_wrap(Smem& sm) {
       const int oi = __shfl_xor_sync(kFull, wr.qi, o);
       wr.offer(ox, oz, oi);
     }
+    // Wrap::offer is not symmetric under rounding (on nearly collinear points two lanes of a butterfly pair can
+    // each keep their own candidate), so the lanes may end with different winners: lane 0's is THE next vertex.
+    // Without this the lanes would leave the loop at different steps and the next shuffle would never complete.
+    wr.qx = __shfl_sync(kFull, wr.qx, 0); wr.qz = __shfl_sync(kFull, wr.qz, 0); wr.qi = __shfl_sync(kFull, wr.qi, 0);
     if (wr.qi < 0) break;                                           // every point coincides
     if (wr.qx == sx0 && wr.qz == sz0) { closed = true; break; }     // wrapped around
     wr.cx = wr.qx; wr.cz = wr.qz; cur = wr.qi;

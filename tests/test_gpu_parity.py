@@ -242,6 +242,35 @@ def test_fit_points_golden(ops, golden, method):
             close(rec[orc.O_BOX2D:orc.O_BOX2D + 4], proj, 1e-6 * max(1.0, np.abs(uv).max()))
 
 
+def test_fit_points_tied_hull_edges(ops):
+    """Rectangular lattices at several rotations and regular n-gons (tests/golden/golden_ties_v1.npz, from the
+    unmodified reference).  Every hull edge of such a footprint gives the same bounding rectangle area up to the
+    last bits, so WHICH edge wins depends on the rounding of sin / cos and on the hull's starting vertex (Qhull's
+    is an implementation detail).  Bar: the kernel's yaw is the angle of one of the edges whose area is within 1e-12
+    of the minimum and its box has the reference's footprint area; a footprint with a unique minimal edge must
+    match the reference record."""
+    import os
+
+    import tie_cases
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_ties_v1.npz")) as z:
+        gold = {k: z[k] for k in z.files}
+    for name in gold["names"]:
+        pc = gold[f"{name}/pc"]
+        rec = ops.fit_points(dev(pc), dev(np.array([0, len(pc)]), torch.int64), None, None, None, "convex_hull").cpu().numpy()[0]
+        assert int(rec[orc.O_STATUS]) == orc.ST_OK, name
+        areas, yaws = tie_cases.edge_search(pc)
+        tied = areas <= areas.min() * (1 + 1e-12)
+        assert np.abs(yaws[tied] - rec[orc.O_YAW]).min() < 1e-12, (name, rec[orc.O_YAW], yaws[tied])
+        ref = gold[f"{name}/dims"]
+        assert abs(ref[0] * ref[2] - rec[orc.O_DIM] * rec[orc.O_DIM + 2]) <= 1e-11 * ref[0] * ref[2], name
+        assert abs(ref[1] - rec[orc.O_DIM + 1]) <= 1e-12, name
+        if tied.sum() == 1 or abs(rec[orc.O_YAW] - float(gold[f"{name}/yaw"])) < 1e-12:
+            close(rec[orc.O_VERT:orc.O_VERT + 24].reshape(8, 3), gold[f"{name}/vertices"], 1e-11)
+            close(rec[orc.O_CENTER:orc.O_CENTER + 3], gold[f"{name}/center"], 1e-11)
+            close(rec[orc.O_DIM:orc.O_DIM + 3], gold[f"{name}/dims"], 1e-11)
+            close(rec[orc.O_RCAM:orc.O_RCAM + 9].reshape(3, 3), gold[f"{name}/R_cam"], 1e-9)
+
+
 def test_fit_points_batch_and_errors(ops, golden):
     """Several ragged point sets in one launch, including the reference's error cases."""
     rng = np.random.RandomState(2)
