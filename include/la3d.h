@@ -173,6 +173,10 @@ int la3d_sample_ranks(const uint32_t* chunk_counts, const void* prep, int B, int
  *   bits / chunk_counts / ranks: outputs of la3d_mask_scan and la3d_sample_ranks
  *   records [B*I][64] float (rec_f64 = 0) or double (rec_f64 = 1)
  * ------------------------------------------------------------------------- */
+/* Debug aid: when set (device pointer to [boxes][8] int64, or NULL to switch off), thread 0 of every CTA of the
+ * scanned-mask fit kernel stores clock64() at 8 phase boundaries (start, prologue, gather, octagon, yaw, extents,
+ * record, stores): per-phase latency without a profiler (tools/fit_phases.py). */
+void la3d_debug_fit_clocks(long long* clocks);
 int la3d_fit_scanned(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
                      const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps, void* records,
                      int rec_f64, la3d_stream_t stream);

@@ -46,6 +46,9 @@ struct FitArgs {
   const PrepCamera* cams;   // [images] intrinsics and their inverse (la3d_fit_prepare)
   const double* Rg_pre;     // [boxes][9] ground rotations (la3d_fit_prepare)
   int I, HW, W, chunks;
+  int search_top;           // largest power of two <= chunks - 1 (find_chunks)
+  uint32_t w_magic;         // p / W for p < 2^30 as umulhi(p, w_magic) >> w_shift; 0: W == 1
+  int w_shift;
   // explicit-point source
   const double* pts;
   const int64_t* offsets;
@@ -54,6 +57,7 @@ struct FitArgs {
   const double* K;        // [images or boxes][9] intrinsics; may be null for explicit points
   const double* ground;   // [boxes][3] or null
   int method, yaw_steps, n_areas;
+  long long* phase_clocks;  // debug (la3d_debug_fit_clocks): [boxes][8] clock64 stamps of thread 0, or null
   int box0;               // first box of this launch (a step may be cut into several launches over one set of buffers)
   RecordSink sink;        // one local buffer, or the gathered buffers of all ranks (peer memory); sink.cuh
 };
@@ -65,6 +69,8 @@ struct Smem {
   double red[kWarps][8];
   double Kinv[9], Kmat[9], Rg[9];
   int oct_idx[8];                              // extreme points of the footprint (octagon, CCW): indices into x / z
+  double octx[8], octz[8], oct_cx, oct_cz;     // their coordinates and centre
+  float pre[8][4];                             // float32 inside test per octagon edge (yaw_common.cuh)
   double yaw, cos_yaw, sin_yaw;
   int ired[kWarps][4];
   int cand_n, hull_n;
@@ -204,25 +210,32 @@ __device__ void octagon_candidates(Smem& sm, int nsel) {
       if (f[d] == e[d]) atomicMin(&sm.oct_idx[d], k);
   }
   __syncthreads();
-  double ox[8], oz[8];
-#pragma unroll
-  for (int d = 0; d < 8; ++d) {
-    const int k = min(sm.oct_idx[d], nsel - 1);        // always elected: e[d] is attained by a valid point
-    ox[d] = sm.x[k]; oz[d] = sm.z[k];
+  if (threadIdx.x < 8) {
+    const int k = min(sm.oct_idx[threadIdx.x], nsel - 1);        // always elected: e[d] is attained by a valid point
+    sm.octx[threadIdx.x] = sm.x[k]; sm.octz[threadIdx.x] = sm.z[k];
+    __syncwarp(0xffu);
+    double cx = 0.0, cz = 0.0;                                    // every edge thread sums the centre itself (same order)
+    for (int d = 0; d < 8; ++d) { cx += sm.octx[d]; cz += sm.octz[d]; }
+    cx /= 8; cz /= 8;
+    if (threadIdx.x == 0) { sm.oct_cx = cx; sm.oct_cz = cz; }
+    polygon_pretest_edge(sm.octx, sm.octz, 8, cx, cz, threadIdx.x, sm.pre[threadIdx.x]);
   }
+  __syncthreads();
+  float pa[8], pb[8], pc[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) { pa[d] = sm.pre[d][0]; pb[d] = sm.pre[d][1]; pc[d] = sm.pre[d][2]; }
+  const double ccx = sm.oct_cx, ccz = sm.oct_cz;
   for (int k0 = 0; k0 < nsel; k0 += kThreads) {
     const int k = k0 + threadIdx.x;
     bool keep = false;
     if (k < nsel) {
       const double px = sm.x[k], pz = sm.z[k];
       if (px == px) {
+        // float32 test with a rounding margin: passing every edge = strictly inside the octagon
+        const float fx = (float)(px - ccx), fz = (float)(pz - ccz);
         bool inside = true;
 #pragma unroll
-        for (int d = 0; d < 8; ++d) {
-          const int n = (d + 1) & 7;
-          const double ex = ox[n] - ox[d], ez = oz[n] - oz[d];
-          if (ex != 0.0 || ez != 0.0) inside = inside && (ex * (pz - oz[d]) - ez * (px - ox[d]) > 0.0);
-        }
+        for (int d = 0; d < 8; ++d) inside = inside && (fmaf(pa[d], fx, fmaf(pb[d], fz, pc[d])) > 0.f);
         keep = !inside;
       }
     }
@@ -292,25 +305,27 @@ __device__ __forceinline__ double edge_angle(const Smem& sm, int hn, int e) {
 }
 
 // ---- gather: rank -> pixel -> depth -> camera point ---------------------------------------
-// Branch-free binary search with a uniform step count, so that the searches of a thread's
-// samples interleave (independent shared-memory loads per step).
+// Branch-free search for the chunk holding rank r: the largest c with pref[c] <= r.  Uniform step count, so that
+// the searches of a thread's samples interleave (independent shared-memory loads per step).  `top` is the largest
+// power of two <= chunks - 1 (0 for one chunk): the first probe folds the non-power-of-two remainder, every later
+// probe pos + half stays below chunks.
 template <int G>
-__device__ __forceinline__ void find_chunks(const uint32_t* pref, int chunks, int steps, const uint32_t (&r)[G],
+__device__ __forceinline__ void find_chunks(const uint32_t* pref, int chunks, int top, const uint32_t (&r)[G],
                                             int (&chunk)[G], uint32_t (&rem)[G]) {
-  int lo[G], hi[G];
+  int pos[G];
+  const int first = chunks - 1 - top;                           // >= 0; pref[first + top] is the last chunk's offset
 #pragma unroll
-  for (int j = 0; j < G; ++j) { lo[j] = 0; hi[j] = chunks; }    // invariant: pref[lo] <= r < pref[hi]
-  for (int s = 0; s < steps; ++s) {
+  for (int j = 0; j < G; ++j) pos[j] = (top && pref[first + 1] <= r[j]) ? first + 1 : 0;   // invariant: pref[pos] <= r
+  // after the first probe the answer lies in [pos, pos + top): halve
+  for (int half = top >> 1; half > 0; half >>= 1) {
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-      const int mid = (lo[j] + hi[j]) >> 1;                     // == lo once the interval has closed
-      const bool right = pref[mid] <= r[j];
-      lo[j] = right ? mid : lo[j];
-      hi[j] = right ? hi[j] : mid;
+      const int nxt = pos[j] + half;
+      pos[j] = (pref[nxt] <= r[j]) ? nxt : pos[j];
     }
   }
 #pragma unroll
-  for (int j = 0; j < G; ++j) { chunk[j] = lo[j]; rem[j] = r[j] - pref[lo[j]]; }
+  for (int j = 0; j < G; ++j) { chunk[j] = pos[j]; rem[j] = r[j] - pref[pos[j]]; }
 }
 
 // ---- the kernel ------------------------------------------------------------------------
@@ -329,6 +344,8 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
 
   const int box = blockIdx.x + a.box0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  auto stamp = [&](int i) { if (a.phase_clocks && tid == 0) a.phase_clocks[(size_t)box * 8 + i] = clock64(); };
+  stamp(0);
   const int img = kScanned ? box / a.I : box;
 
   if (kScanned) {
@@ -349,7 +366,9 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   const double* src_pts = nullptr;
   const uint32_t* cc = nullptr;
   if (kScanned) {
-    // exclusive prefix over the chunk totals; each thread owns a contiguous run
+    // exclusive prefix over the chunk totals; each thread owns a contiguous run.  (Keeping the quarter-count words
+    // in shared memory as well, to save the samples' scattered global load of them, measured 40 % slower on B200:
+    // more shared memory per CTA and more live registers in the gather loop.)
     cc = a.chunk_counts + (size_t)box * a.chunks;
     const int per = (a.chunks + kThreads - 1) / kThreads;
     const int c_lo = min(tid * per, a.chunks), c_hi = min(c_lo + per, a.chunks);
@@ -381,6 +400,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
     pdl_wait();
   }
 
+  stamp(1);                                    // prologue (cameras, chunk prefix) done
   const bool subsample = n_src > LA3D_SUBSAMPLE;
   int status = LA3D_ST_OK;
   if (!kScanned && subsample && !a.sample_idx) status = LA3D_ST_TOO_MANY;
@@ -392,8 +412,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   // The kGroup samples of a thread advance through the dependent loads together.
   int n_valid = 0, inf_xz = 0, inf_y = 0;
   double y_lo = CUDART_INF, y_hi = -CUDART_INF;
-  int search_steps = 0;
-  if (kScanned) while ((1 << search_steps) < a.chunks) ++search_steps;
+  const int search_top = a.search_top;
   for (int k0 = tid; k0 < nsel; k0 += kThreads * kGroup) {
     double X[kGroup], Y[kGroup], Z[kGroup];
     if (kScanned) {
@@ -405,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
       }
       int chunk[kGroup];
       uint32_t rem[kGroup];
-      find_chunks<kGroup>(pref, a.chunks, search_steps, r, chunk, rem);
+      find_chunks<kGroup>(pref, a.chunks, search_top, r, chunk, rem);
       uint32_t qw[kGroup];
 #pragma unroll
       for (int j = 0; j < kGroup; ++j) qw[j] = __ldg(cc + chunk[j]);
@@ -445,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
       }
 #pragma unroll
       for (int j = 0; j < kGroup; ++j) {
-        const int v = p[j] / a.W, u = p[j] - v * a.W;
+        const int v = a.w_magic ? (int)(__umulhi((uint32_t)p[j], a.w_magic) >> a.w_shift) : p[j], u = p[j] - v * a.W;
         lift_pixel_exact((double)d[j], (double)u, (double)v, sm.Kinv, X[j], Y[j], Z[j]);
       }
     } else {
@@ -484,6 +503,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
     block_sum_int(r, sm);           // its barriers also publish sm.x / y / z
     n_valid = r[0]; inf_xz = r[1]; inf_y = r[2];
   }
+  stamp(2);                                    // gather + lift + alignment done
   if (status == LA3D_ST_OK) {
     // same order as the reference: the NaN filter raises first (:142-143), then the method check (:151)
     if (n_valid == 0) status = LA3D_ST_NO_VALID;
@@ -504,6 +524,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   } else {
     octagon_candidates(sm, nsel);
     const int nc = sm.cand_n;
+    stamp(3);                                  // octagon filter done
     if (a.method == LA3D_METHOD_CONVEX_HULL) {
       if (warp == 0) hull_wrap(sm);
       __syncthreads();
@@ -532,6 +553,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
     }
   }
   __syncthreads();
+  stamp(4);                                    // yaw known
   const double yaw = sm.yaw;
 
   // ---- extents at that yaw: rotate_y(yaw) @ pc^T, per-axis min / max (:154-160) ------
@@ -550,14 +572,20 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   const double dim[3] = {ext[3] - ext[0], ext[4] - ext[1], ext[5] - ext[2]};
   const double ctr[3] = {(ext[0] + ext[3]) / 2, (ext[1] + ext[4]) / 2, (ext[2] + ext[5]) / 2};
 
+  stamp(5);                                    // extents done
   write_box_record(dim, ctr, yaw, cy_, sy_, sm.Rg, sm.Kmat, kScanned || a.K != nullptr, sm.rec, n_valid, n_src, tid);
   }
+  stamp(6);                                    // record built
   sink_acquire(a.sink);
   sink_store(a.sink, (size_t)box, sm.rec, kThreads);
   sink_release(a.sink);
+  stamp(7);
 }
 
+long long* g_phase_clocks = nullptr;
+
 int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s, bool pdl = false) {
+  a.phase_clocks = scanned ? g_phase_clocks : nullptr;
   a.n_areas = a.method == LA3D_METHOD_SWEEP ? (a.yaw_steps > 0 ? a.yaw_steps : 1)
             : a.method == LA3D_METHOD_CONVEX_HULL ? kMaxPts : 0;
   a.n_areas = (a.n_areas + 1) & ~1;                       // keep what follows 16-byte aligned
@@ -597,12 +625,23 @@ int fit_scanned_sink(const float* depth, const void* prep, const uint32_t* bits,
   a.depth = depth; a.bits = bits; a.chunk_counts = chunk_counts; a.ranks = ranks;
   a.cams = pv.cams; a.Rg_pre = pv.Rg;
   a.I = I; a.HW = H * W; a.W = W; a.chunks = (int)la3d_chunks_per_plane(H, W);
+  a.search_top = 0;
+  while (a.chunks - 1 >= 2 * (a.search_top ? a.search_top : 1) || (a.search_top == 0 && a.chunks > 1)) a.search_top = a.search_top ? a.search_top * 2 : 1;
+  // exact division of any p < 2^30 by W: M = ceil(2^(30+s) / W), s = max(2, ceil(log2 W)), q = (p * M) >> (30 + s)
+  if (W > 1) {
+    int sh = 2;
+    while ((1ll << sh) < W) ++sh;
+    a.w_magic = (uint32_t)(((1ull << (30 + sh)) + (uint64_t)W - 1) / (uint64_t)W);
+    a.w_shift = sh - 2;
+  }
   a.method = method; a.yaw_steps = yaw_steps;
   a.box0 = b0 * I;
   a.sink = sink;
   return launch_fit(true, a, Bp * I, stream, pdl);
 }
 }  // namespace la3d
+
+extern "C" void la3d_debug_fit_clocks(long long* clocks) { la3d::g_phase_clocks = clocks; }
 
 extern "C" int la3d_fit_scanned(const float* depth, const void* prep, const uint32_t* bits,
                                 const uint32_t* chunk_counts, const int32_t* ranks, int B, int I, int H, int W,

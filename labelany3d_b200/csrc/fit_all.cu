@@ -303,24 +303,7 @@ __device__ __forceinline__ void build_pretest(Smem& sm) {
     sm.npre = (n >= 3 && n <= 8) ? n : 0;
   }
   __syncthreads();
-  if (d < 8 && sm.npre) {
-    float a = 0.f, b = 0.f, c = 1.f;                        // unused slots always pass
-    if (d < n) {
-      double radius = 0.0;
-      for (int i = 0; i < n; ++i)
-        radius = fmax(radius, fmax(fabs(sm.polyx[i] - sm.pre_cx), fabs(sm.polyz[i] - sm.pre_cz)));
-      const int e = (d + 1 == n) ? 0 : d + 1;
-      const double ox = sm.polyx[d] - sm.pre_cx, oz = sm.polyz[d] - sm.pre_cz;
-      const double ex = sm.polyx[e] - sm.polyx[d], ez = sm.polyz[e] - sm.polyz[d];
-      a = (float)(-ez); b = (float)ex;
-      const double c0 = -((double)a * ox + (double)b * oz);
-      const double margin = ldexp((fabs((double)a) + fabs((double)b)) * 2.0 * radius, -19);
-      c = (float)(c0 - margin);
-      if (!(fabsf(a) < CUDART_INF_F) || !(fabsf(b) < CUDART_INF_F) || !(fabsf(c) < CUDART_INF_F)) { a = 0.f; b = 0.f; c = -1.f; }
-      else c = nextafterf(c, -CUDART_INF_F);                 // the rounding of c itself
-    }
-    sm.pre[d][0] = a; sm.pre[d][1] = b; sm.pre[d][2] = c; sm.pre[d][3] = 0.f;
-  }
+  if (d < 8 && sm.npre) polygon_pretest_edge(sm.polyx, sm.polyz, n, sm.pre_cx, sm.pre_cz, d, sm.pre[d]);
   __syncthreads();
 }
 

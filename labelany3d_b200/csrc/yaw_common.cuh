@@ -54,6 +54,7 @@ __device__ __forceinline__ double rect_area(const double* __restrict__ x, const 
   sincos(ang, &s, &c);
   if (kind) s = -s;
   double mnx = CUDART_INF, mxx = -CUDART_INF, mnz = CUDART_INF, mxz = -CUDART_INF;
+#pragma unroll 4
   for (int k = 0; k < n; ++k) {
     const int idx = list ? list[k] : k;
     const double px = x[idx], pz = z[idx];
@@ -61,6 +62,35 @@ __device__ __forceinline__ double rect_area(const double* __restrict__ x, const 
     mnx = dmin(mnx, rx); mxx = dmax(mxx, rx); mnz = dmin(mnz, rz); mxz = dmax(mxz, rz);
   }
   return (mxx - mnx) * (mxz - mnz);
+}
+
+// float32 form of "strictly inside a convex polygon of n <= 8 vertices (counter-clockwise; consecutive duplicates
+// allowed)", safe under rounding.  One thread per edge d < 8 writes pre[d] = {a, b, c}: a point p passes edge d when
+// a * x' + b * z' + c > 0 with (x', z') = float(p - centre).  c carries a margin that covers the rounding of a, b, c,
+// x', z' and of the two FMAs for every point within twice the polygon's radius of its centre, and points farther
+// out fail some edge by much more than any rounding; so a point that passes ALL edges lies strictly inside the
+// polygon (it cannot be extreme in any direction), while a point that fails is merely kept.  Degenerate edges
+// (repeated vertex) and unused slots always pass.  The caller synchronises between writing the vertices / centre
+// and calling this, and again before using pre[].
+__device__ __forceinline__ void polygon_pretest_edge(const double* __restrict__ vx, const double* __restrict__ vz, int n,
+                                                     double cx, double cz, int d, float (&out)[4]) {
+  float a = 0.f, b = 0.f, c = 1.f;
+  if (d < n) {
+    const int e = (d + 1 == n) ? 0 : d + 1;
+    const double ex = vx[e] - vx[d], ez = vz[e] - vz[d];
+    if (ex != 0.0 || ez != 0.0) {
+      double radius = 0.0;
+      for (int i = 0; i < n; ++i) radius = fmax(radius, fmax(fabs(vx[i] - cx), fabs(vz[i] - cz)));
+      const double ox = vx[d] - cx, oz = vz[d] - cz;
+      a = (float)(-ez); b = (float)ex;
+      const double c0 = -((double)a * ox + (double)b * oz);
+      const double margin = ldexp((fabs((double)a) + fabs((double)b)) * 2.0 * radius, -19);
+      c = (float)(c0 - margin);
+      if (!(fabsf(a) < CUDART_INF_F) || !(fabsf(b) < CUDART_INF_F) || !(fabsf(c) < CUDART_INF_F)) { a = 0.f; b = 0.f; c = -1.f; }   // never passes
+      else c = nextafterf(c, -CUDART_INF_F);                // the rounding of c itself
+    }
+  }
+  out[0] = a; out[1] = b; out[2] = c; out[3] = 0.f;
 }
 
 __device__ __forceinline__ double sweep_angle(int c, int K) {

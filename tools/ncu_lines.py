@@ -19,7 +19,7 @@ rep, kregex, mangled = sys.argv[1:4]
 skip = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "labelany3d_b200", "lib", "libla3d_sm100a.so")
+so = os.environ.get("LA3D_SO", os.path.join(root, "labelany3d_b200", "lib", "libla3d_sm100a.so"))
 
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kregex}", "-s", str(skip), "-c", "1"],
                      capture_output=True, text=True).stdout
@@ -79,7 +79,7 @@ src_cache = {}
 def src(loc):
     f, n = loc
     for d in ("labelany3d_b200/csrc", "include"):
-        p = os.path.join(root, d, f)
+        p = os.path.join(os.environ.get("LA3D_SRC_ROOT", root), d, f)
         if os.path.isfile(p):
             if p not in src_cache:
                 src_cache[p] = open(p).read().splitlines()
