@@ -2,9 +2,10 @@
 // (src/util.py:52-75 of the reference).  HBM-bound: 4 B read + 12 B (float) or
 // 24 B (double) written per pixel.
 //
-// lift_prep_kernel + lift_bulk_kernel (the fast path): the cameras of all images
-// (inverse intrinsics, optional rigid transform) are prepared once per launch by one
-// thread per image into a stream-ordered scratch buffer.  One CTA of 128 threads then
+// lift_bulk_kernel (the fast path).  Cameras (inverse intrinsics, optional rigid transform): for
+// short launches every CTA prepares its image's camera itself while its depth loads are in
+// flight; for long ones lift_prep_kernel prepares all of them once, one thread per image, into a
+// stream-ordered scratch buffer (the threshold was measured, see the kernel).  One CTA of 128 threads
 // owns a tile of 1536 (float) / 1024 (double) consecutive pixels of one image: each
 // thread issues its 16-byte depth loads, reads its image's camera (uniform loads),
 // converts, and writes its points into the CTA's shared-memory tile; one thread hands
@@ -199,11 +200,17 @@ __global__ void __launch_bounds__(kThreads, kMinCtas)
 // instruction.  Here the CTA assembles its tile of points in shared memory and ONE thread hands
 // the whole contiguous tile (up to 48 KB) to the TMA unit (cp.async.bulk shared -> global), which
 // writes full lines.  One CTA = kQuads x kT x 4 consecutive pixels of one image.
-template <bool kF64, int kQuads, int kT>
+// kOwnCam: every CTA prepares its image's camera itself (one thread, while the depth loads are in flight) - no
+// preparation launch and no scratch buffer, which wins for short launches (configs[1]: 206 vs 216 us per call);
+// otherwise the cameras come from lift_prep_kernel's buffer, which wins when the launch is long enough to amortise
+// the extra launch (configs[3]: 730 vs 763 us).
+template <bool kF64, int kQuads, int kT, bool kOwnCam>
 __global__ void __launch_bounds__(kT)
-    lift_bulk_kernel(const float* __restrict__ depth, const Camera* __restrict__ cams, int has_R, int has_t, int HW,
+    lift_bulk_kernel(const float* __restrict__ depth, const Camera* __restrict__ cams, const double* __restrict__ K,
+                     int k_stride, int k_is_inverse, const double* __restrict__ R, const double* __restrict__ t, int HW,
                      int W, int tiles_per_image, void* __restrict__ out_) {
   extern __shared__ __align__(128) unsigned char stage_raw[];
+  __shared__ Camera scam;
   constexpr int kStep = kT * 4;
   constexpr int kTilePx = kQuads * kStep;
   const int b = blockIdx.x / tiles_per_image;
@@ -216,16 +223,21 @@ __global__ void __launch_bounds__(kT)
   for (int q = 0; q < kQuads; ++q)
     dq[q] = (px + q * kStep < HW) ? ld_stream(reinterpret_cast<const float4*>(img + px + q * kStep))
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-  const Camera* gc = cams + b;
+  if (kOwnCam) {
+    if (threadIdx.x == 0) prepare_camera(scam, K + (size_t)b * k_stride, k_is_inverse, R, t);
+    __syncthreads();
+  }
+  const Camera* gc = kOwnCam ? &scam : cams + b;
+  const int has_R = R != nullptr, has_t = t != nullptr;
   Camera cam;
   if (kF64) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) cam.Kinv[i] = __ldg(&gc->Kinv[i]);
+    for (int i = 0; i < 9; ++i) cam.Kinv[i] = kOwnCam ? gc->Kinv[i] : __ldg(&gc->Kinv[i]);
   } else {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) cam.M[i] = __ldg(&gc->M[i]);
+    for (int i = 0; i < 9; ++i) cam.M[i] = kOwnCam ? gc->M[i] : __ldg(&gc->M[i]);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) cam.t[i] = __ldg(&gc->t[i]);
+    for (int i = 0; i < 3; ++i) cam.t[i] = kOwnCam ? gc->t[i] : __ldg(&gc->t[i]);
   }
   const double* Rp = has_R ? gc->R : nullptr;
   const double* tp = has_t ? gc->t : nullptr;
@@ -291,14 +303,15 @@ __global__ void __launch_bounds__(kThreads) lift_scalar_kernel(const float* __re
 }
 
 template <bool kF64, int kQ, int kT>
-int launch_bulk(const float* depth, const Camera* cams, const double* R, const double* t, int B, int HW, int W,
-                void* out, cudaStream_t s) {
+int launch_bulk(const float* depth, const Camera* cams, const double* K, int k_stride, int k_is_inverse, const double* R,
+                const double* t, int B, int HW, int W, void* out, cudaStream_t s) {
   constexpr int kTilePx = kQ * kT * 4;
   constexpr int kSmem = kTilePx * 3 * (kF64 ? 8 : 4);
   const int tiles = (HW + kTilePx - 1) / kTilePx;
   LA3D_REQUIRE((long long)tiles * B < (1ll << 31), "grid too large");
-  static_assert(kSmem <= 48 * 1024, "tile must fit the default dynamic shared memory limit");
-  lift_bulk_kernel<kF64, kQ, kT><<<(unsigned)(tiles * B), kT, kSmem, s>>>(depth, cams, R != nullptr, t != nullptr, HW, W, tiles, out);
+  static_assert(kSmem + sizeof(Camera) <= 48 * 1024, "tile + camera must fit the default shared memory limit");
+  if (cams) lift_bulk_kernel<kF64, kQ, kT, false><<<(unsigned)(tiles * B), kT, kSmem, s>>>(depth, cams, K, k_stride, k_is_inverse, R, t, HW, W, tiles, out);
+  else lift_bulk_kernel<kF64, kQ, kT, true><<<(unsigned)(tiles * B), kT, kSmem, s>>>(depth, nullptr, K, k_stride, k_is_inverse, R, t, HW, W, tiles, out);
   return LA3D_OK;
 }
 
@@ -323,35 +336,37 @@ extern "C" int la3d_depth_lift(const float* depth, const double* K, int k_stride
   const int HW = H * W;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool vec = (HW % 4 == 0) && aligned16(depth) && aligned16(out);
+  const int variant = lift_variant();
+  // short launches: every CTA prepares its own camera; long ones: one preparation launch into a stream-ordered scratch
+  const bool own_cam = variant != 0 && (long long)B * HW <= 150000000ll;
   Camera* cams = nullptr;
-  if (vec && cudaMallocAsync(reinterpret_cast<void**>(&cams), sizeof(Camera) * (size_t)B, s) != cudaSuccess) {
-    cudaGetLastError();   // no stream-ordered pool on this driver: use the self-contained fallback below
+  if (vec && !own_cam && cudaMallocAsync(reinterpret_cast<void**>(&cams), sizeof(Camera) * (size_t)B, s) != cudaSuccess) {
+    cudaGetLastError();   // no stream-ordered pool on this driver: the CTAs prepare their cameras themselves
     cams = nullptr;
   }
-  if (cams) {
-    // cameras once per launch (B threads), then one CTA per 4096-pixel tile of one image
-    lift_prep_kernel<<<(B + 127) / 128, 128, 0, s>>>(K, k_stride, k_is_inverse, R, t, B, cams);
-    const int tiles = (HW + kQuads * kStepPx - 1) / (kQuads * kStepPx);
-    LA3D_REQUIRE((long long)tiles * B < (1ll << 31), "grid too large");
-    const unsigned grid = (unsigned)(tiles * B);
-    const int variant = lift_variant();
+  if (vec && (cams || variant != 0)) {
+    if (cams) lift_prep_kernel<<<(B + 127) / 128, 128, 0, s>>>(K, k_stride, k_is_inverse, R, t, B, cams);
     if (variant == 0) {
+      // LA3D_LIFT_VARIANT=0: direct stores, one CTA per 4096-pixel tile of one image
+      const int tiles = (HW + kQuads * kStepPx - 1) / (kQuads * kStepPx);
+      LA3D_REQUIRE((long long)tiles * B < (1ll << 31), "grid too large");
+      const unsigned grid = (unsigned)(tiles * B);
       if (out_f64)
         lift_tile_kernel<true, kQuads, kMinCtas><<<grid, kThreads, 0, s>>>(depth, cams, R != nullptr, t != nullptr, HW, W, tiles, out);
       else
         lift_tile_kernel<false, kQuads, kMinCtas><<<grid, kThreads, 0, s>>>(depth, cams, R != nullptr, t != nullptr, HW, W, tiles, out);
     } else {
-      int rc = LA3D_OK;
       // tile sizes measured on B200 (tools/lift_variants.py): 1536-pixel tiles (18 KB) for float,
-      // 1024-pixel tiles (24 KB) for double; variant 2 = 2048-pixel tiles for both
-      if (variant == 2) rc = out_f64 ? launch_bulk<true, 4, 128>(depth, cams, R, t, B, HW, W, out, s)
-                                     : launch_bulk<false, 4, 128>(depth, cams, R, t, B, HW, W, out, s);
-      else rc = out_f64 ? launch_bulk<true, 2, 128>(depth, cams, R, t, B, HW, W, out, s)
-                        : launch_bulk<false, 3, 128>(depth, cams, R, t, B, HW, W, out, s);
+      // 1024-pixel tiles (24 KB) for double; variant 2 = 2048- / 1536-pixel tiles
+      int rc = LA3D_OK;
+      if (variant == 2) rc = out_f64 ? launch_bulk<true, 3, 128>(depth, cams, K, k_stride, k_is_inverse, R, t, B, HW, W, out, s)
+                                     : launch_bulk<false, 4, 128>(depth, cams, K, k_stride, k_is_inverse, R, t, B, HW, W, out, s);
+      else rc = out_f64 ? launch_bulk<true, 2, 128>(depth, cams, K, k_stride, k_is_inverse, R, t, B, HW, W, out, s)
+                        : launch_bulk<false, 3, 128>(depth, cams, K, k_stride, k_is_inverse, R, t, B, HW, W, out, s);
       if (rc) return rc;
     }
     LA3D_CUDA(cudaGetLastError());
-    LA3D_CUDA(cudaFreeAsync(cams, s));
+    if (cams) LA3D_CUDA(cudaFreeAsync(cams, s));
   } else {
     LA3D_REQUIRE(B <= 65535, "fallback path supports at most 65535 images per call");
     dim3 grid((unsigned)min((HW + kThreads - 1) / kThreads, 4096), (unsigned)B);
