@@ -24,8 +24,8 @@ void set_error(const char* fmt, ...) {
 // fit's prologue overlap the kernel before them).  Off by default: measured on B200 it costs 17 us per
 // step (204 vs 187 us) - the early-scheduled CTAs sit in griddepcontrol.wait on slots the scan's last
 // waves would have used.
-static bool pdl_enabled() {
-  static const bool v = getenv("LA3D_PDL") && atoi(getenv("LA3D_PDL")) != 0;
+static int pdl_mode() {
+  static const int v = getenv("LA3D_PDL") ? atoi(getenv("LA3D_PDL")) : 0;   // 1: sampler and fit, 2: the fit only
   return v;
 }
 
@@ -193,10 +193,10 @@ static int run_step(Produce&& produce, const float* depth, const double* K, cons
     const PrepArgs pa{K, ground, B, I, seed0, pv};
     int rc = produce(0, B, pa);
     if (rc) return rc;
-    rc = launch_sample(w.chunk_counts, pv, B, I, chunks, w.counts, w.ranks, stream, pdl_enabled());
+    rc = launch_sample(w.chunk_counts, pv, B, I, chunks, w.counts, w.ranks, stream, pdl_mode() == 1);
     if (rc) return rc;
     return fit_scanned_sink(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, sink, stream,
-                            pdl_enabled());
+                            pdl_mode() != 0);
   }
   Pipe* pipe = nullptr;
   if (int rc = pipe_get(&pipe)) return rc;
@@ -263,7 +263,7 @@ __global__ void peer_sync_kernel(RecordSink s, int do_signal, int do_wait) {
     __threadfence_system();
     st_release_sys(s.flags[p] + s.rank, s.epoch);
   }
-  if (do_wait) wait_flag(s.flags[s.rank] + p, s.epoch, s.status, s.timeout_ns);
+  if (do_wait) wait_flag<true>(s.flags[s.rank] + p, s.epoch, s.status, s.timeout_ns);
 }
 
 static int peer_sync(uint32_t* const* flags, int rank, int world, uint32_t epoch, int32_t* status, int do_signal,

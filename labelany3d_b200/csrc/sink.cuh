@@ -44,6 +44,18 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// no L1 invalidation behind it (an acquire load carries a CCTL.IVALL): for waits that only gate later STORES
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// release-only increment: MEMBAR.ALL.SYS + ATOMG, no L1 invalidation (unlike __threadfence_system + atomicAdd)
+__device__ __forceinline__ uint32_t atom_add_release_sys(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.add.release.sys.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -51,12 +63,17 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 // Spin until *flag has reached `epoch` (epochs only grow; compared modulo 2^32).  A peer that does not
 // show up within the timeout is fatal: the sticky status word is set and the kernel traps, so the
 // failure surfaces as a CUDA error on the host instead of as stale records.
+// kAcquire: the wait precedes READS of what the peers wrote (la3d_peer_wait); otherwise it only gates later stores
+// (the fit kernels' wait before they overwrite peer buffers) and a relaxed load does, which spares the SM's other
+// CTAs the L1 invalidation an acquire load brings.
+template <bool kAcquire>
 __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, int32_t* status,
                                           unsigned long long timeout_ns) {
-  if ((int32_t)(ld_acquire_sys(flag) - epoch) >= 0) return;
+  auto peek = [&]() { return kAcquire ? ld_acquire_sys(flag) : ld_relaxed_sys(flag); };
+  if ((int32_t)(peek() - epoch) >= 0) return;
   const unsigned long long t0 = global_ns();
   for (;;) {
-    if ((int32_t)(ld_acquire_sys(flag) - epoch) >= 0) return;
+    if ((int32_t)(peek() - epoch) >= 0) return;
     if (global_ns() - t0 > timeout_ns) {
       if (status) { *reinterpret_cast<volatile int32_t*>(status) = 1; __threadfence_system(); }
       __trap();
@@ -69,7 +86,7 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, 
 // sink synchronises peers).
 __device__ __forceinline__ void sink_acquire(const RecordSink& s) {
   if (!s.flags[0]) return;
-  if (threadIdx.x < s.n_out) wait_flag(s.flags[s.rank] + threadIdx.x, s.epoch - 1u, s.status, s.timeout_ns);
+  if (threadIdx.x < s.n_out) wait_flag<false>(s.flags[s.rank] + threadIdx.x, s.epoch - 1u, s.status, s.timeout_ns);
   __syncthreads();
 }
 
@@ -105,16 +122,19 @@ __device__ __forceinline__ void fill_failed_record(double* __restrict__ rec, int
   }
 }
 
-// Called by every thread of the CTA after its last sink_store.
+// Called by every thread of the CTA after its last sink_store.  Release chain: the CTA's stores -> block barrier ->
+// thread 0's release increment of the local counter (system scope: the stores went to peers); the CTA that completes
+// the count acquires the others' increments with one fence and publishes the epoch with release stores.  Only that one
+// CTA pays a full fence (whose L1 invalidation would otherwise hit every co-resident CTA once per box: measured
+// ~30 us per step on B200 when every CTA used __threadfence_system).
 __device__ __forceinline__ void sink_release(const RecordSink& s) {
   if (!s.flags[0]) return;
-  __syncthreads();                                   // every store of the CTA is ordered before thread 0's fence
+  __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
-    const uint32_t done = atomicAdd(s.counter, 1u);
+    const uint32_t done = atom_add_release_sys(s.counter, 1u);
     if (done == (s.total_ctas ? s.total_ctas : gridDim.x) - 1u) {
-      *s.counter = 0u;                               // ready for the next launch
-      __threadfence_system();                        // the other CTAs' fenced stores are ordered before the flags
+      *s.counter = 0u;                               // ready for the next launch (stream-ordered after this kernel)
+      __threadfence_system();
       for (int p = 0; p < s.n_out; ++p) st_release_sys(s.flags[p] + s.rank, s.epoch);
     }
   }
