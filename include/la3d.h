@@ -376,6 +376,27 @@ int la3d_masked_ratio_median(const float* depth_map, const float* depth_render, 
                              const uint32_t* render_bits, int planes, int group, int H, int W, int32_t* n_overlap,
                              float* scale, la3d_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Depth-stage scale alignment ("next" row f3, second half): the arithmetic of align_depth,
+ * src/batch_scripts/depth.py:52-92 = RANSACRegressor(LinearRegression(fit_intercept=False), min_samples=0.2).fit
+ * on x = relative_depth[valid], y = metric_depth[valid] (float32, row-major order of the valid pixels).  The
+ * host draws each trial's subset exactly as scikit-learn does and drives the loop (dropin/depth_align.py):
+ *   la3d_ransac_subset_fit  sums[0] = sum x^2, sums[1] = sum x y over x[idx[k]], y[idx[k]], k < m (float64):
+ *                           the least-squares slope through the origin is sums[1] / sums[0]
+ *   la3d_ransac_classify    residual |y - x*coef| in float32 (no FMA, as NumPy evaluates y - X @ coef), inlier iff
+ *                           <= threshold; stats[0..5] = n_inliers, sum y, sum y^2, sum residual^2, sum x^2, sum x y
+ *                           over the inliers (float64; score and final refit)
+ *   la3d_scale_fill         out[i] = mask[i] (or, mask NULL, !isinf(rel[i])) ? rel[i]*coef : fill   (:82-90)
+ * The reference's slope comes out of LAPACK's float32 least squares, which is not restated: parity with the reference
+ * is statistical (same subsets, slopes within ~1e-6 relative), parity with the oracle's restatement is exact.
+ * ------------------------------------------------------------------------- */
+int la3d_ransac_subset_fit(const float* x, const float* y, const int64_t* idx, long long m, double* sums,
+                           la3d_stream_t stream);
+int la3d_ransac_classify(const float* x, const float* y, long long n, float coef, float threshold, double* stats,
+                         la3d_stream_t stream);
+int la3d_scale_fill(const float* rel, const uint8_t* mask, long long n, float coef, float fill, float* out,
+                    la3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,9 @@ SIGNATURES = {
     "la3d_fit_boxes_rle": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u32, _u32, _vp, _sz, _vp, _vp, _i, _vp]),
     "la3d_fit_all_points": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "la3d_fit_boxes_all": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp, _i, _vp]),
+    "la3d_ransac_subset_fit": (_i, [_vp, _vp, _vp, C.c_longlong, _vp, _vp]),
+    "la3d_ransac_classify": (_i, [_vp, _vp, C.c_longlong, C.c_float, C.c_float, _vp, _vp]),
+    "la3d_scale_fill": (_i, [_vp, _vp, C.c_longlong, C.c_float, C.c_float, _vp, _vp]),
     "la3d_project_points": (_i, [_vp, _vp, _vp, C.c_longlong, _vp, _vp]),
 }
 

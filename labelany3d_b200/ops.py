@@ -701,5 +701,58 @@ def depth_scale_median(depth_map, depth_render, mask_bits, render_bits, H, W):
     return n, scale
 
 
+def ransac_subset_fit(x, y, idx):
+    """Least-squares slope through the origin of the pairs ``(x[idx], y[idx])`` (``la3d_ransac_subset_fit``): what
+    ``LinearRegression(fit_intercept=False).fit`` computes for one RANSAC trial of the reference's ``align_depth``
+    (``src/batch_scripts/depth.py:52-92``).  ``x``, ``y`` float32 CUDA vectors, ``idx`` int64 CUDA vector.  Returns
+    the slope as a Python float rounded to float32 (one device synchronisation: the loop on the host needs it)."""
+    lib = _lib.load()
+    x = _need_cuda("x", x, torch.float32)
+    y = _need_cuda("y", y, torch.float32)
+    idx = _need_cuda("idx", idx, torch.int64)
+    sums = torch.empty(2, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.la3d_ransac_subset_fit(_ptr(x), _ptr(y), _ptr(idx), idx.numel(), _ptr(sums), _stream())
+    _lib.check(rc, "la3d_ransac_subset_fit")
+    sxx, sxy = sums.tolist()
+    return float(np.float32(sxy / sxx))
+
+
+def ransac_classify(x, y, coef, threshold):
+    """``stats[6]`` (NumPy float64) of one RANSAC trial over ALL pairs (``la3d_ransac_classify``): number of inliers
+    (``|y - x*coef| <= threshold`` in float32), and over the inliers sum y, sum y^2, sum residual^2, sum x^2, sum x y."""
+    lib = _lib.load()
+    stats = torch.empty(6, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.la3d_ransac_classify(_ptr(x), _ptr(y), x.numel(), float(coef), float(threshold), _ptr(stats), _stream())
+    _lib.check(rc, "la3d_ransac_classify")
+    return stats.cpu().numpy()
+
+
+def scale_fill(rel, mask, coef, fill=10000.0):
+    """``out = where(mask, rel * coef, fill)`` in float32 (``la3d_scale_fill``); ``mask=None``: ``~isinf(rel)``."""
+    lib = _lib.load()
+    rel = _need_cuda("rel", rel, torch.float32)
+    m8 = None
+    if mask is not None:
+        m8, _ = _masks_u8(_need_cuda("mask", mask))
+    out = torch.empty_like(rel)
+    with torch.cuda.device(rel.device):
+        rc = lib.la3d_scale_fill(_ptr(rel), _ptr(m8), rel.numel(), float(coef), float(fill), _ptr(out), _stream())
+    _lib.check(rc, "la3d_scale_fill")
+    return out
+
+
+def median_f32(values):
+    """Exact ``np.median`` of a float32 CUDA vector (float32 result, even counts average the two middle values in
+    float32): the radix-select kernel of the depth-scale row (``la3d_masked_ratio_median``) on ``values / 1``."""
+    values = _need_cuda("values", values, torch.float32)
+    n = values.numel()
+    ones = torch.ones((1, 1, 1, n), dtype=torch.float32, device=values.device)
+    bits, _ = mask_scan(torch.ones((1, 1, n), dtype=torch.bool, device=values.device))
+    _, scale = depth_scale_median(values.view(1, 1, n), ones, bits, bits, 1, n)
+    return scale[0, 0]
+
+
 def to_numpy(t):
     return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)

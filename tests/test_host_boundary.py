@@ -79,6 +79,9 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
         "la3d_fit_boxes_rle": lambda: lib.la3d_fit_boxes_rle(None, None, None, 0, None, None, None, 1, 1, 4, 4, 0, 0, 0, 0, None, 0, None, None, 0, None),
         "la3d_fit_all_points": lambda: lib.la3d_fit_all_points(None, None, None, 1, 1, 4, 4, None, 0, None),
         "la3d_fit_boxes_all": lambda: lib.la3d_fit_boxes_all(None, None, None, None, 1, 1, 4, 4, 1, None, 0, None, 0, None),
+        "la3d_ransac_subset_fit": lambda: lib.la3d_ransac_subset_fit(None, None, None, 1, None, None),
+        "la3d_ransac_classify": lambda: lib.la3d_ransac_classify(None, None, 1, 1.0, 1.0, None, None),
+        "la3d_scale_fill": lambda: lib.la3d_scale_fill(None, None, 1, 1.0, 1.0, None, None),
         "la3d_masked_ratio_median": lambda: lib.la3d_masked_ratio_median(None, None, None, None, 1, 1, 4, 4, None, None, None),
     }
     for name, call in calls.items():
