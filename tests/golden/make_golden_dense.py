@@ -3,7 +3,8 @@ Run in the build container:
 
     python tests/golden/make_golden_dense.py
 
-The all-pixels mode is the reference's ``estimate_bbox`` (``src/util_3dbox.py:106-178``, ``method='pca'``) with
+The all-pixels mode is the reference's ``estimate_bbox`` (``src/util_3dbox.py:106-178``, ``method='pca'`` and
+``method='convex_hull'``: keys ``records`` / ``records_hull``) with
 its random 500-point draw (``:123-125``) replaced by the identity.  That is exactly what this script makes the
 unmodified reference function compute: while it runs, ``numpy.random.randint`` (the one name the draw goes
 through) returns ``arange(high)``, so ``in_pc[rand_ind]`` is ``in_pc``.  Inputs: the composed scene of
@@ -27,7 +28,7 @@ import live_reference  # noqa: E402
 from oracle import la3d_oracle as orc  # noqa: E402
 
 
-def reference_records(util, box, comb, depth, K, masks, ground):
+def reference_records(util, box, comb, depth, K, masks, ground, method="pca"):
     B, I = masks.shape[:2]
     rec = np.full((B, I, orc.REC), np.nan)
     real_randint = np.random.randint
@@ -41,7 +42,7 @@ def reference_records(util, box, comb, depth, K, masks, ground):
                 g = None if ground is None else ground[b, i]
                 try:
                     with live_reference.quiet(), np.errstate(invalid="ignore", over="ignore"):
-                        v, ctr, dim, Rc = box.estimate_bbox(pc, None, g, "pca")
+                        v, ctr, dim, Rc = box.estimate_bbox(pc, None, g, method)
                 except ValueError as exc:
                     rec[b, i] = orc.failed_record(orc.status_of_exception(exc), np.nan, pc.shape[0])
                     continue
@@ -61,18 +62,19 @@ def main():
     worst = {}
     for name, (depth, K, masks, ground) in dense_cases.scenes().items():
         for use_ground in (0, 1):
+          for method, key in (("pca", "records"), ("convex_hull", "records_hull")):
             g = ground if use_ground else None
-            rec = reference_records(util, box, comb, depth, K, masks, g)
-            G[f"{name}/g{use_ground}/records"] = rec
+            rec = reference_records(util, box, comb, depth, K, masks, g, method)
+            G[f"{name}/g{use_ground}/{key}"] = rec
             for impl in ("library", "closed"):
-                mine = orc.fit_boxes(depth, K, masks, g, "pca", impl=impl, subsample=False)
+                mine = orc.fit_boxes(depth, K, masks, g, method, impl=impl, subsample=False)
                 a, b = mine[..., sel], rec[..., sel]
                 same = np.isnan(a) & np.isnan(b)
                 scale = np.maximum(1.0, np.nanmax(np.abs(np.where(np.isfinite(b), b, 0.0)), axis=-1, keepdims=True))
                 d = np.where(same, 0.0, np.abs(a - b) / scale)
                 worst[impl] = max(worst.get(impl, 0.0), float(np.nanmax(d)))
                 assert not np.isnan(d).any(), (name, use_ground, impl)
-            print(name, use_ground, "pixels per mask", rec[..., orc.O_NMASK].astype(int).tolist(), "status",
+            print(name, use_ground, method, "pixels per mask", rec[..., orc.O_NMASK].astype(int).tolist(), "status",
                   rec[..., orc.O_STATUS].astype(int).tolist())
     assert worst["library"] == 0.0, worst
     assert worst["closed"] < 1e-9, worst

@@ -55,6 +55,20 @@ def test_all_pixels_fit_matches_the_reference(ops):
             assert (np.abs(a - b) <= np.maximum(TOL_PRODUCT, 1.2e-7 * np.abs(b))).all()
 
 
+def test_all_pixels_hull_matches_the_reference(ops):
+    """method='convex_hull' over every masked pixel against the records the unmodified reference produced with its
+    draw replaced by the identity (golden_dense_v1.npz, keys records_hull)."""
+    with np.load(os.path.join(ROOT, "tests", "golden", "golden_dense_v1.npz")) as z:
+        gold = {k: z[k] for k in z.files}
+    for name, (depth, K, masks, ground) in dense_cases.scenes().items():
+        for use_ground in (0, 1):
+            ref = gold[f"{name}/g{use_ground}/records_hull"]
+            g = dev(ground) if use_ground else None
+            rec = ops.fit_boxes_all(dev(depth), dev(K), dev(masks), g, method="convex_hull").cpu().numpy()
+            np.testing.assert_array_equal(rec[..., orc.O_STATUS], ref[..., orc.O_STATUS], err_msg=name)
+            check_record(rec, ref, TOL_F64)
+
+
 def test_small_masks_equal_the_sampled_path(ops):
     """At most 500 pixels: the reference does not draw, so both kernels must describe the same box."""
     depth, K, masks, ground = dense_cases.scenes()["composed"]

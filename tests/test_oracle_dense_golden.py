@@ -20,6 +20,22 @@ def gold():
 
 
 @pytest.mark.parametrize("impl", ["library", "closed"])
+def test_all_pixels_hull_oracle_matches_the_reference(gold, impl):
+    """method='convex_hull' over ALL masked points (keys records_hull: the unmodified reference with the identity draw)."""
+    sel = np.ones(orc.REC, dtype=bool)
+    sel[[orc.O_YAW, orc.O_NVALID]] = False
+    for name, (depth, K, masks, ground) in dense_cases.scenes().items():
+        for use_ground in (0, 1):
+            ref = gold[f"{name}/g{use_ground}/records_hull"]
+            mine = orc.fit_boxes(depth, K, masks, ground if use_ground else None, "convex_hull", impl=impl, subsample=False)
+            np.testing.assert_array_equal(mine[..., orc.O_STATUS], ref[..., orc.O_STATUS])
+            for a, b in zip(mine.reshape(-1, orc.REC), ref.reshape(-1, orc.REC)):
+                fin = b[sel][np.isfinite(b[sel])]
+                scale = max(1.0, float(np.abs(fin).max())) if fin.size else 1.0
+                close(a[sel], b[sel], (0.0 if impl == "library" else 1e-9) * scale)
+
+
+@pytest.mark.parametrize("impl", ["library", "closed"])
 def test_all_pixels_oracle_matches_the_reference(gold, impl):
     sel = np.ones(orc.REC, dtype=bool)
     sel[[orc.O_YAW, orc.O_NVALID]] = False
