@@ -266,17 +266,18 @@ int la3d_fit_boxes_all(const float* depth, const uint8_t* masks, const double* K
  *     the per-process results): records[p] = rank p's gathered record buffer + THIS rank's slot (include the
  *     local one), peer-mapped; the box kernel stores every record straight into all n_out buffers over NVLink,
  *     so the all-gather of the packed records costs no extra pass.  The cross-GPU
- *     synchronisation is done by the same kernel:
+ *     synchronisation rides in the step's own launches:
  *       flags[p]  rank p's flag row, >= n_out uint32, peer-mapped, zero-initialised once
- *       counter   one uint32 of LOCAL device memory, zero-initialised once
+ *       counter   unused (reserved)
  *       status    nullable int32 in host-visible (pinned) or device memory, zero-initialised once
  *       epoch     the step number: 1 for the first call, growing by one per call, the same on every rank
  *       rank      this rank's index (its column in every flag row)
- *     Before its first store a CTA waits until every slot of flags[rank] has reached epoch-1 (the peers are
- *     past the step that last read the buffers about to be overwritten: alternate between TWO gathered
- *     buffers per rank, and consume a gathered buffer on the stream that issues the next call); the last
- *     CTA of the grid to finish stores `epoch` into slot `rank` of every rank's row (release, system scope).
- *     A consumer of the gathered records first waits for la3d_peer_wait(flags, rank, n_out, epoch).
+ *     Before its first store a CTA of the box kernel waits until every slot of flags[rank] has reached epoch-1 (the
+ *     peers are past the step that last read the buffers about to be overwritten: alternate between TWO gathered
+ *     buffers per rank, and consume a gathered buffer on the stream that issues the next call).  The box kernel does
+ *     NOT publish its own epoch: the kernel boundary after it guarantees its stores have been performed, so the
+ *     first CTA of the NEXT `_to` call on the stream publishes epoch-1 (one release store per rank), and a consumer of
+ *     the gathered records of step `epoch` first runs la3d_peer_barrier(flags, rank, n_out, epoch) (publish + wait).
  *     A rank without images in a step calls la3d_peer_signal instead of a fit.
  *     A peer that does not arrive within the timeout (default 120 s, LA3D_PEER_TIMEOUT_MS or
  *     la3d_set_peer_timeout_ms) is fatal: *status is set to 1 and the kernel traps, so the host sees a CUDA

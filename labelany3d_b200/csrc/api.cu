@@ -105,7 +105,6 @@ int sink_from_public(const la3d_sink* pub, RecordSink* out) {
   s.n_out = pub->n_out;
   s.rec_f64 = pub->rec_f64 ? 1 : 0;
   if (pub->flags[0]) {
-    LA3D_REQUIRE(pub->counter != nullptr, "peer synchronisation needs the local counter word");
     LA3D_REQUIRE(pub->rank >= 0 && pub->rank < pub->n_out, "rank outside the destinations");
     LA3D_REQUIRE(pub->epoch != 0, "epochs start at 1");
     for (int p = 0; p < pub->n_out; ++p) {
@@ -186,11 +185,17 @@ static int run_step(Produce&& produce, const float* depth, const double* K, cons
                     cudaStream_t stream) {
   const PrepView pv = prep_view(w.prep, B, I, prep_blocks(I));
   const int chunks = (int)la3d_chunks_per_plane(H, W);
+  // the first launch of this step publishes the PREVIOUS step's epoch to the peers (sink.cuh)
+  PeerPublish pub{};
+  if (sink.flags[0] && sink.epoch > 1u) {
+    for (int p = 0; p < sink.n_out; ++p) pub.flags[p] = sink.flags[p];
+    pub.n = sink.n_out; pub.rank = sink.rank; pub.epoch = sink.epoch - 1u;
+  }
   const int per = g_pipe_override >= 0 ? g_pipe_override : pipe_images();
   int parts = per > 0 ? (B + per - 1) / per : 1;
   if (parts > kMaxParts) parts = kMaxParts;
   if (parts <= 1) {
-    const PrepArgs pa{K, ground, B, I, seed0, pv};
+    const PrepArgs pa{K, ground, B, I, seed0, pv, pub};
     int rc = produce(0, B, pa);
     if (rc) return rc;
     rc = launch_sample(w.chunk_counts, pv, B, I, chunks, w.counts, w.ranks, stream, pdl_mode() == 1);
@@ -201,13 +206,12 @@ static int run_step(Produce&& produce, const float* depth, const double* K, cons
   Pipe* pipe = nullptr;
   if (int rc = pipe_get(&pipe)) return rc;
   std::lock_guard<std::mutex> lock(pipe->mu);             // one enqueue sequence at a time per device
-  sink.total_ctas = (uint32_t)B * (uint32_t)I;            // the release fires after the last CTA of the last part
   const int step = (B + parts - 1) / parts;
   bool used[2] = {false, false};
   for (int p = 0, b0 = 0; b0 < B; ++p, b0 += step) {
     const int Bp = b0 + step <= B ? step : B - b0;
     const PrepArgs pa{K + (size_t)b0 * 9, ground ? ground + (size_t)b0 * I * 3 : nullptr, Bp, I, seed0 + (uint32_t)b0,
-                      prep_part(pv, b0, I)};
+                      prep_part(pv, b0, I), p == 0 ? pub : PeerPublish{}};
     int rc = produce(b0, Bp, pa);
     if (rc) return rc;
     cudaStream_t side = pipe->side[p & 1];
@@ -277,6 +281,17 @@ static int peer_sync(uint32_t* const* flags, int rank, int world, uint32_t epoch
   }
   s.n_out = world; s.rank = rank; s.epoch = epoch; s.status = status; s.timeout_ns = peer_timeout_ns();
   peer_sync_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(s, do_signal, do_wait);
+  LA3D_CUDA(cudaGetLastError());
+  return LA3D_OK;
+}
+}  // namespace la3d
+
+namespace la3d {
+int publish_previous_epoch(const RecordSink& sink, cudaStream_t stream) {
+  if (!sink.flags[0] || sink.epoch <= 1u) return LA3D_OK;
+  RecordSink s = sink;
+  s.epoch = sink.epoch - 1u;
+  peer_sync_kernel<<<1, 32, 0, stream>>>(s, 1, 0);
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
 }
@@ -419,7 +434,12 @@ static int fit_boxes_all_sink(const float* depth, const uint8_t* masks, const do
     return LA3D_ENOMEM;
   }
   const PrepView pv = prep_view(w.prep, B, I, prep_blocks(I));
-  const PrepArgs pa{K, ground, B, I, 0u, pv};              // cameras and ground rotations; the random words go unused
+  PeerPublish pub{};
+  if (sink.flags[0] && sink.epoch > 1u) {
+    for (int p = 0; p < sink.n_out; ++p) pub.flags[p] = sink.flags[p];
+    pub.n = sink.n_out; pub.rank = sink.rank; pub.epoch = sink.epoch - 1u;
+  }
+  const PrepArgs pa{K, ground, B, I, 0u, pv, pub};         // cameras and ground rotations; the random words go unused
   int rc = launch_mask_scan(masks, B * I, H, W, mask_is_01, w.bits, w.chunk_counts, &pa, static_cast<cudaStream_t>(stream));
   if (rc) return rc;
   return fit_all_sink(depth, w.prep, w.bits, B, I, H, W, method, yaw_steps, sink, static_cast<cudaStream_t>(stream));

@@ -658,6 +658,7 @@ extern "C" int la3d_fit_scanned_to(const float* depth, const void* prep, const u
   using namespace la3d;
   RecordSink rs;
   if (int rc = sink_from_public(sink, &rs)) return rc;
+  if (int rc = publish_previous_epoch(rs, static_cast<cudaStream_t>(stream))) return rc;
   return fit_scanned_sink(depth, prep, bits, chunk_counts, ranks, B, I, H, W, method, yaw_steps, rs,
                           static_cast<cudaStream_t>(stream), false);
 }

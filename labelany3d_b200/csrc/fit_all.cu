@@ -688,5 +688,6 @@ extern "C" int la3d_fit_all_points_to(const float* depth, const void* prep, cons
   using namespace la3d;
   RecordSink rs;
   if (int rc = sink_from_public(sink, &rs)) return rc;
+  if (int rc = publish_previous_epoch(rs, static_cast<cudaStream_t>(stream))) return rc;
   return fit_all_sink(depth, prep, bits, B, I, H, W, method, yaw_steps, rs, static_cast<cudaStream_t>(stream));
 }

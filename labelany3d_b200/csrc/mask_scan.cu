@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kThreads, kPrep ? 8 : 1)
   int bid = blockIdx.x;
   if (kPrep) {
     const int prep_ctas = (pa.B + kWarps - 1) / kWarps;           // one warp per image
+    if (bid == 0) publish_epoch(pa.pub);
     if (bid < prep_ctas) { prep_body<kThreads>(pa, bid * kWarps); return; }     // CTA-uniform
     bid -= prep_ctas;
   }

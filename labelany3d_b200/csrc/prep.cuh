@@ -9,13 +9,29 @@ namespace la3d {
 
 constexpr int kMtM = 397;
 
+// Multi-GPU: the launch that OPENS a step also publishes the previous step's epoch in every rank's flag row (sink.cuh):
+// at a kernel boundary every record the previous fit kernel stored into peer memory has been performed, so one
+// thread's release store does what a fence + counter in every fit CTA would.
+struct PeerPublish {
+  uint32_t* flags[LA3D_MAX_PEERS];
+  int n, rank;            // n == 0: nothing to publish
+  uint32_t epoch;
+};
+
 struct PrepArgs {
   const double* K;        // [B][9]
   const double* ground;   // [B*I][3] or null
   int B, I;
   uint32_t seed0;         // image b seeds with seed0 + b (mod 2^32)
   PrepView pv;
+  PeerPublish pub;
 };
+
+// First preparation CTA of a launch: threads 0 .. n-1 publish (no-op without peers).
+__device__ __forceinline__ void publish_epoch(const PeerPublish& pub) {
+  if ((int)threadIdx.x < pub.n)
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pub.flags[threadIdx.x] + pub.rank), "r"(pub.epoch) : "memory");
+}
 
 __device__ __forceinline__ uint32_t twist(uint32_t cur, uint32_t nxt) {
   uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) rle_decode_kernel(RleArgs 
   int plane = blockIdx.x;
   if (kPrep) {
     const int prep_ctas = (pa.B + kWarps - 1) / kWarps;           // one warp per image
+    if (plane == 0) publish_epoch(pa.pub);
     if (plane < prep_ctas) { prep_body<kThreads, true>(pa, plane * kWarps, dyn); return; }   // CTA-uniform
     plane -= prep_ctas;
   }

@@ -1,14 +1,18 @@
 // Where the records of a box kernel go: one local buffer, or this rank's slot in the gathered record
 // buffer of EVERY rank of an NVLink / NVSwitch node (peer-mapped memory), with the cross-GPU
-// synchronisation done by the kernel itself:
-//   acquire  before its first peer store a CTA makes sure every rank has published epoch - 1 in this
-//            rank's flag row: the peers are then past the step that last READ the buffers about to be
-//            overwritten (the gathered buffers are double-buffered by the caller);
+// synchronisation folded into the step's own launches:
+//   acquire  before its first peer store a CTA of the box kernel makes sure every rank has published epoch - 1 in
+//            this rank's flag row: the peers are then past the step that last READ the buffers about to be
+//            overwritten (the gathered buffers are double-buffered by the caller).  A relaxed load: it only gates
+//            later stores, and an acquire load would invalidate the SM's L1 under the other resident CTAs;
 //   store    the 64 fields of a record, 16 bytes per store, to every destination;
-//   release  the last CTA of the grid to finish (a counter in local memory) publishes `epoch` in the
-//            flag row of every rank (st.release.sys after a system-scope fence).
-// A consumer of the gathered records waits until every slot of ITS flag row has reached the epoch
-// (la3d_peer_wait).  No side stream, no event edge, no extra launch on the producer's stream.
+//   release  NOT in the box kernel: the kernel boundary after it already guarantees that its stores have been
+//            performed, so the epoch is published by the first CTA of the NEXT launch on the stream - the next
+//            step's scan / decode (PeerPublish, prep.cuh) or the consumer's la3d_peer_barrier - with one release
+//            store per rank.  (A fence + counter increment in every fit CTA, the first form, measured +6 us per step
+//            on one GPU and its full-fence variant +30 us: MEMBAR.SYS / CCTL.IVALL once per box.)
+// A consumer of the gathered records first runs la3d_peer_barrier: publish this rank's epoch, wait until every slot
+// of ITS flag row has reached it.  No side stream, no event edge.
 #pragma once
 
 #include <math_constants.h>
@@ -20,7 +24,7 @@ namespace la3d {
 struct RecordSink {
   void* out[LA3D_MAX_PEERS];          // record buffers: box j goes to out[p] + j * 64 elements, every p < n_out
   uint32_t* flags[LA3D_MAX_PEERS];    // flags[p] = rank p's flag row; flags[0] == nullptr: no peer synchronisation
-  uint32_t* counter;                  // one word of local memory, zero between launches
+  uint32_t* counter;                  // unused since 0.2.1 (kept for the layout of la3d_sink)
   int32_t* status;                    // sticky error word (host-visible), set to 1 before a timeout trap
   unsigned long long timeout_ns;
   uint32_t epoch;
@@ -32,6 +36,9 @@ struct RecordSink {
 RecordSink local_sink(void* records, int rec_f64);
 int sink_from_public(const la3d_sink* pub, RecordSink* out);
 unsigned long long peer_timeout_ns();
+// For entry points without an opening launch of their own (la3d_fit_scanned_to, la3d_fit_all_points_to): publish the
+// previous step's epoch with a one-CTA launch before the box kernel.
+int publish_previous_epoch(const RecordSink& sink, cudaStream_t stream);
 
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
@@ -122,22 +129,8 @@ __device__ __forceinline__ void fill_failed_record(double* __restrict__ rec, int
   }
 }
 
-// Called by every thread of the CTA after its last sink_store.  Release chain: the CTA's stores -> block barrier ->
-// thread 0's release increment of the local counter (system scope: the stores went to peers); the CTA that completes
-// the count acquires the others' increments with one fence and publishes the epoch with release stores.  Only that one
-// CTA pays a full fence (whose L1 invalidation would otherwise hit every co-resident CTA once per box: measured
-// ~30 us per step on B200 when every CTA used __threadfence_system).
-__device__ __forceinline__ void sink_release(const RecordSink& s) {
-  if (!s.flags[0]) return;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t done = atom_add_release_sys(s.counter, 1u);
-    if (done == (s.total_ctas ? s.total_ctas : gridDim.x) - 1u) {
-      *s.counter = 0u;                               // ready for the next launch (stream-ordered after this kernel)
-      __threadfence_system();
-      for (int p = 0; p < s.n_out; ++p) st_release_sys(s.flags[p] + s.rank, s.epoch);
-    }
-  }
-}
+// Called by every thread of the CTA after its last sink_store.  Nothing to do: the release happens at the next
+// launch boundary (see the header comment).
+__device__ __forceinline__ void sink_release(const RecordSink&) {}
 
 }  // namespace la3d

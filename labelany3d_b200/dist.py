@@ -106,12 +106,13 @@ class PeerGather:
         self._lib_mod.check(rc, "la3d_peer_signal")
 
     def wait(self):
-        """The current stream waits until the records of the last step have landed from every rank."""
+        """The current stream publishes this rank's epoch (the box kernel leaves that to the next launch on the stream)
+        and waits until the records of the last step have landed from every rank."""
         if self.epoch:
             with torch.cuda.device(self.device):
-                rc = self._lib.la3d_peer_wait(self._flag_ptrs, self.rank, self.world, self.epoch & 0xFFFFFFFF,
-                                              self._status.data_ptr(), torch.cuda.current_stream().cuda_stream)
-            self._lib_mod.check(rc, "la3d_peer_wait")
+                rc = self._lib.la3d_peer_barrier(self._flag_ptrs, self.rank, self.world, self.epoch & 0xFFFFFFFF,
+                                                 self._status.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            self._lib_mod.check(rc, "la3d_peer_barrier")
 
     def check(self):
         """Raises if a peer failed to arrive within the timeout (no device synchronisation: the word is in
@@ -128,10 +129,10 @@ class ShardedBoxFitter:
     ``collective="p2p"`` (default on CUDA with more than one rank): the gathered ``[world*per, I, 64]``
     buffer of every rank lives in symmetric (peer-mapped) memory and the fit kernel of rank ``r``
     writes its records directly into slot ``r`` of EVERY rank's buffer over NVLink
-    (``la3d_fit_boxes_to``).  The cross-GPU synchronisation is inside the same kernel (flag rows in peer
-    memory: acquire before the first store, release by the last CTA), so a step adds no launch, no
-    side stream and no NCCL call to the data path; a consumer waits with :meth:`wait_gathered`
-    (``wait=True`` does it in the call).  The gathered buffer is double-buffered: the tensor a call
+    (``la3d_fit_boxes_to``).  The cross-GPU synchronisation rides in the step's own launches (flag rows in peer
+    memory: the fit kernel waits before its first peer store, the next step's scan publishes the epoch), so a
+    step adds no launch, no side stream and no NCCL call to the data path; a consumer publishes and waits with
+    :meth:`wait_gathered` (``wait=True`` does it in the call).  The gathered buffer is double-buffered: the tensor a call
     returns stays valid until the next-but-one call (consume it on the same stream).
     ``collective="nccl"``: one ``all_gather_into_tensor`` after the fit (the plain form).
     ``source``: ``"masks"`` (byte masks, the default), ``"rle"`` (COCO run-length annotations:
