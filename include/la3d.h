@@ -67,7 +67,9 @@ typedef void* la3d_stream_t; /* cudaStream_t */
 #define LA3D_O_UV 42     /* 8x2 projected corners                util.py:227-229       */
 #define LA3D_O_BOX2D 58  /* [min u, min v, max u, max v]         tools/combine_results.py:241-246 */
 #define LA3D_O_NMASK 62  /* pixels set in the mask / points given */
-#define LA3D_O_PAD 63
+#define LA3D_O_PAD 63   /* flags: 0, or LA3D_FLAG_HULL_FALLBACK */
+#define LA3D_FLAG_HULL_FALLBACK 1 /* method convex_hull: no hull (coincident / collinear points, Qhull raises in the
+                                    reference, util_3dbox.py:222-224): the yaw is the PCA yaw */
 
 int la3d_version(void);
 const char* la3d_last_error(void);

@@ -17,7 +17,7 @@ namespace la3d {
 __device__ __forceinline__ void write_box_record(const double (&dim)[3], const double (&ctr)[3], double yaw, double cy_,
                                                  double sy_, const double* __restrict__ Rg,
                                                  const double* __restrict__ Kmat, bool has_K, double* __restrict__ rec,
-                                                 int n_valid, long long n_src, int tid) {
+                                                 int n_valid, long long n_src, int tid, double flags = 0.0) {
   // rotate_y(-yaw) = [[c,0,-s],[0,1,0],[s,0,c]] with c = cos(yaw), s = sin(yaw)
   const double Ry[9] = {cy_, 0.0, -sy_, 0.0, 1.0, 0.0, sy_, 0.0, cy_};
   if (tid < 8) {
@@ -63,7 +63,7 @@ __device__ __forceinline__ void write_box_record(const double (&dim)[3], const d
     rec[LA3D_O_NVALID] = (double)n_valid;
     rec[LA3D_O_STATUS] = (double)LA3D_ST_OK;
     rec[LA3D_O_NMASK] = (double)n_src;
-    rec[LA3D_O_PAD] = 0.0;
+    rec[LA3D_O_PAD] = flags;
   } else if (tid == 40) {
     // R_cam = Rg^T @ rotate_y(-yaw)  (:176)
 #pragma unroll

@@ -518,6 +518,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   } else {
   // ---- yaw ---------------------------------------------------------------------------
   bool have_trig = false;          // yaw_pca leaves cos / sin of the yaw in shared memory
+  bool hull_fallback = false;
   if (a.method == LA3D_METHOD_PCA) {
     yaw_pca(sm, nsel, n_valid);
     have_trig = true;
@@ -532,6 +533,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
       if (hn == 0) {
         yaw_pca(sm, nsel, n_valid);                    // Qhull would have raised (QH6214 / QH6154): fall back
         have_trig = true;
+        hull_fallback = true;                          // reported in the record (LA3D_FLAG_HULL_FALLBACK)
       } else {
         // util_3dbox.py:202-218: one thread per hull edge, first strict minimum of the area
         for (int e = tid; e < hn; e += kThreads) areas[e] = rect_area(sm.x, sm.z, sm.hull, hn, edge_angle(sm, hn, e), 0);
@@ -573,7 +575,8 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   const double ctr[3] = {(ext[0] + ext[3]) / 2, (ext[1] + ext[4]) / 2, (ext[2] + ext[5]) / 2};
 
   stamp(5);                                    // extents done
-  write_box_record(dim, ctr, yaw, cy_, sy_, sm.Rg, sm.Kmat, kScanned || a.K != nullptr, sm.rec, n_valid, n_src, tid);
+  write_box_record(dim, ctr, yaw, cy_, sy_, sm.Rg, sm.Kmat, kScanned || a.K != nullptr, sm.rec, n_valid, n_src, tid,
+                   hull_fallback ? (double)LA3D_FLAG_HULL_FALLBACK : 0.0);
   }
   stamp(6);                                    // record built
   sink_acquire(a.sink);

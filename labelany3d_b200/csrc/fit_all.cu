@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(kThreads) fit_all_kernel(AllArgs a) {
     __syncthreads();
   } else {
   // ---- yaw -------------------------------------------------------------------------------------------
-  bool have_trig = false;
+  bool have_trig = false, hull_fallback = false;
   if (!kSearch || a.method == LA3D_METHOD_PCA) {
     if (tid == 0) yaw_from_moments(s, n_valid, sm);
     have_trig = true;
@@ -567,6 +567,7 @@ __global__ void __launch_bounds__(kThreads) fit_all_kernel(AllArgs a) {
       if (hn == 0) {
         if (tid == 0) yaw_from_moments(s, n_valid, sm);                // Qhull would have raised: fall back to PCA
         have_trig = true;
+        hull_fallback = true;
       } else {
         // util_3dbox.py:202-218: one thread per hull edge, first strict minimum of the area
         auto edge_angle = [&](int e) {
@@ -623,7 +624,8 @@ __global__ void __launch_bounds__(kThreads) fit_all_kernel(AllArgs a) {
   const double ctr[3] = {(ext[0] + ext[3]) / 2, (ext[1] + ext[4]) / 2, (ext[2] + ext[5]) / 2};
 
   // ---- tail (box_tail.cuh: util_3dbox.py:165-176, util.py:227-229) ----
-  write_box_record(dim, ctr, yaw, cy_, sy_, sm.Rg, sm.Kmat, true, sm.rec, n_valid, n_src, tid);
+  write_box_record(dim, ctr, yaw, cy_, sy_, sm.Rg, sm.Kmat, true, sm.rec, n_valid, n_src, tid,
+                   hull_fallback ? (double)LA3D_FLAG_HULL_FALLBACK : 0.0);
   }
   sink_acquire(a.sink);
   sink_store(a.sink, (size_t)box, sm.rec, kThreads);

@@ -111,6 +111,8 @@ def estimate_bbox(in_pc, cat_name=None, ground_equ=None, method='pca', yaw_steps
     err = _rec.status_error(r["status"], method, r["n_valid"])
     if err is not None:
         raise err
+    if r["hull_fallback"]:          # the reference prints Qhull's own message here (:222-224); the event is what matters
+        print("ConvexHull failed: degenerate footprint (coincident or collinear points), falling back to PCA")
     dz, dy, dx = (np.float64(v) for v in r["dimensions"])
     if verbose:
         print(f"[{method}] dx={dx:.3f}, dy={dy:.3f}, dz={dz:.3f}")
@@ -125,6 +127,8 @@ def _yaw_only(rotated_pc, method):
     err = _rec.status_error(r["status"], method, r["n_valid"])
     if err is not None:
         raise err
+    if r["hull_fallback"]:
+        print("ConvexHull failed: degenerate footprint (coincident or collinear points), falling back to PCA")
     return np.float64(r["yaw"])
 
 

@@ -11,6 +11,8 @@ O_UV, O_BOX2D, O_NMASK, O_PAD = 42, 58, 62, 63
 
 ST_OK, ST_NO_VALID, ST_PCA_UNDEFINED, ST_BAD_METHOD, ST_NONFINITE, ST_TOO_MANY = 0, 1, 2, 3, 4, 5
 
+FLAG_HULL_FALLBACK = 1      # O_PAD: method convex_hull found no hull and used the PCA yaw (util_3dbox.py:222-224)
+
 METHODS = {"pca": 0, "convex_hull": 1, "sweep": 2}
 SUBSAMPLE = 500
 
@@ -51,6 +53,7 @@ def unpack(record):
         "corners_2d": r[O_UV:O_UV + 16].reshape(8, 2),
         "bbox2D_proj": r[O_BOX2D:O_BOX2D + 4].copy(),
         "n_mask": int(r[O_NMASK]),
+        "hull_fallback": bool(np.isfinite(r[O_PAD]) and int(r[O_PAD]) & FLAG_HULL_FALLBACK),
     }
 
 

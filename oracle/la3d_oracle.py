@@ -293,8 +293,8 @@ def _hull_search(xz, hull_xy):
     return best_yaw
 
 
-def yaw_from_hull(pc, impl="scipy", verbose=False):
-    """Hull-edge search.  Any hull failure falls back to PCA (``:222-224``)."""
+def yaw_from_hull(pc, impl="scipy", verbose=False, info=None):
+    """Hull-edge search.  Any hull failure falls back to PCA (``:222-224``); ``info["fallback"]`` says so."""
     xz = pc[:, [0, 2]]
     try:
         if impl == "scipy":
@@ -306,6 +306,8 @@ def yaw_from_hull(pc, impl="scipy", verbose=False):
     except Exception as exc:  # noqa: BLE001 - the reference catches everything
         if verbose:
             print(f"ConvexHull failed: {exc}, falling back to PCA")
+        if info is not None:
+            info["fallback"] = True
         return yaw_from_pca(pc, impl="sklearn" if impl == "scipy" else "closed")
 
 
@@ -354,8 +356,9 @@ def fit_details(in_pc, ground_equ=None, method="pca", yaw_steps=None, rng=None, 
         raise ValueError(MSG_NO_VALID)
 
     lib = impl == "library"
+    hull_info = {}
     if method == "convex_hull":
-        yaw = yaw_from_hull(aligned, impl="scipy" if lib else "closed", verbose=verbose)
+        yaw = yaw_from_hull(aligned, impl="scipy" if lib else "closed", verbose=verbose, info=hull_info)
     elif method == "pca":
         yaw = yaw_from_pca(aligned, impl="sklearn" if lib else "closed")
     elif method == "sweep":
@@ -384,7 +387,7 @@ def fit_details(in_pc, ground_equ=None, method="pca", yaw_steps=None, rng=None, 
     R_cam = Rg.T @ yaw_matrix(-yaw)
     return {"vertices": corners, "center_cam": center_cam, "dimension": [dz, dy, dx], "R_cam": R_cam,
             "yaw": float(yaw), "n_valid": len(aligned), "aligned": aligned, "Rg": Rg,
-            "sample_idx": sample_idx}
+            "sample_idx": sample_idx, "hull_fallback": bool(hull_info.get("fallback", False))}
 
 
 def estimate_bbox(in_pc, cat_name=None, ground_equ=None, method="pca", yaw_steps=None,
@@ -492,8 +495,12 @@ def legacy_randint(gen, high, size):
 # --------------------------------------------------------------------------
 # Composition of SURVEY.md section 3.4: depth + masks -> packed box records
 # --------------------------------------------------------------------------
-def pack_record(vertices, center, dims, R_cam, yaw, n_valid, status, uv, box2d, n_mask):
+FLAG_HULL_FALLBACK = 1.0   # O_PAD: the convex-hull method fell back to the PCA yaw (an addition: the reference only prints)
+
+
+def pack_record(vertices, center, dims, R_cam, yaw, n_valid, status, uv, box2d, n_mask, flags=0.0):
     r = np.zeros(REC, dtype=np.float64)
+    r[O_PAD] = flags
     r[O_VERT:O_VERT + 24] = np.asarray(vertices, dtype=np.float64).reshape(-1)
     r[O_CENTER:O_CENTER + 3] = center
     r[O_DIM:O_DIM + 3] = dims
@@ -529,7 +536,7 @@ def fit_points_record(pc, K, ground=None, method="pca", yaw_steps=None, rng=None
         return failed_record(status_of_exception(exc), np.nan, n_mask)
     uv, proj, _ = box2d_from_corners(d["vertices"], K)
     return pack_record(d["vertices"], d["center_cam"], d["dimension"], d["R_cam"], d["yaw"],
-                       d["n_valid"], ST_OK, uv, proj, n_mask)
+                       d["n_valid"], ST_OK, uv, proj, n_mask, FLAG_HULL_FALLBACK if d["hull_fallback"] else 0.0)
 
 
 def fit_boxes(depth, K, masks, ground=None, method="pca", yaw_steps=None, seed=0, image_offset=0,

@@ -201,8 +201,9 @@ def test_sampler_continues_when_pregenerated_words_run_out(ops):
 
 
 # ------------------------------------------------------------------ a3-a8 box from explicit points
-def check_record(rec, ref, tol, skip=(orc.O_YAW, orc.O_NVALID)):
-    """Per box: |diff| <= tol * max(1, largest finite magnitude in the reference record)."""
+def check_record(rec, ref, tol, skip=(orc.O_YAW, orc.O_NVALID, orc.O_PAD)):
+    """Per box: |diff| <= tol * max(1, largest finite magnitude in the reference record).  The default skips what a
+    record minted through the reference API cannot know (yaw, surviving points, the hull-fallback flag)."""
     sel = np.ones(orc.REC, dtype=bool)
     sel[list(skip) + [orc.O_NMASK]] = False
     rec = rec.reshape(-1, orc.REC)
@@ -269,6 +270,26 @@ def test_fit_points_tied_hull_edges(ops):
             close(rec[orc.O_CENTER:orc.O_CENTER + 3], gold[f"{name}/center"], 1e-11)
             close(rec[orc.O_DIM:orc.O_DIM + 3], gold[f"{name}/dims"], 1e-11)
             close(rec[orc.O_RCAM:orc.O_RCAM + 9].reshape(3, 3), gold[f"{name}/R_cam"], 1e-9)
+
+
+def test_hull_fallback_is_flagged(ops):
+    """Collinear and coincident footprints: Qhull raises in the reference, which prints and falls back to the PCA yaw
+    (util_3dbox.py:222-224); the record says so in LA3D_O_PAD, for the sampled and the all-points entry alike."""
+    k = np.arange(40, dtype=np.float64)
+    line = np.stack([1.0 + 0.25 * k, 0.1 * np.sin(k), 4.0 + 0.5 * k], 1)            # exactly collinear in XZ
+    blob = np.random.RandomState(1).normal(size=(60, 3)) * [0.5, 0.1, 0.3] + [0, 0, 5]
+    same = np.tile([[0.5, 0.1, 3.0]], (6, 1)) + [[0, 0.01 * k, 0] for k in range(6)]       # one XZ point, several y
+    sets = [line, blob, same]
+    offsets = np.concatenate([[0], np.cumsum([len(s) for s in sets])])
+    for method, want_flags in (("convex_hull", [1.0, 0.0, None]), ("pca", [0.0, 0.0, None]), ("sweep", [0.0, 0.0, 0.0])):
+        rec = ops.fit_points(dev(np.concatenate(sets)), dev(offsets, torch.int64), None, None, None, method, 12).cpu().numpy()
+        for j, pc in enumerate(sets):
+            if want_flags[j] is None:
+                continue
+            assert rec[j, orc.O_STATUS] == orc.ST_OK and rec[j, orc.O_PAD] == want_flags[j], (method, j, rec[j, orc.O_PAD])
+        if method == "convex_hull":
+            d = orc.fit_details(line, None, "convex_hull", impl="closed")
+            assert d["hull_fallback"] and abs(d["yaw"] - rec[0, orc.O_YAW]) < 1e-9
 
 
 def test_fit_points_batch_and_errors(ops, golden):
