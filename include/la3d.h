@@ -179,6 +179,8 @@ int la3d_sample_ranks(const uint32_t* chunk_counts, const void* prep, int B, int
  * scanned-mask fit kernel stores clock64() at 8 phase boundaries (start, prologue, gather, octagon, yaw, extents,
  * record, stores): per-phase latency without a profiler (tools/fit_phases.py). */
 void la3d_debug_fit_clocks(long long* clocks);
+/* The same for the sampler: [images][4] globaltimer nanoseconds (start, counts totalled, words staged, ranks written). */
+void la3d_debug_sample_clocks(unsigned long long* clocks);
 int la3d_fit_scanned(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
                      const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps, void* records,
                      int rec_f64, la3d_stream_t stream);

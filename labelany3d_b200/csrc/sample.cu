@@ -39,6 +39,14 @@ constexpr int kSegBlocksMax = 16;          // words staged in shared memory at a
 constexpr unsigned kFull = 0xffffffffu;
 
 int g_mt_blocks = 0;                       // 0 = automatic (la3d_set_mt_blocks)
+__device__ unsigned long long* g_sample_clocks = nullptr;   // debug: [images][4] globaltimer stamps (la3d_debug_sample_clocks)
+__device__ __forceinline__ void sample_stamp(int b, int i) {
+  if (g_sample_clocks && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_sample_clocks[(size_t)b * 4 + i] = t;
+  }
+}
 
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepArgs pa) {
   prep_body<kPrepThreads>(pa, blockIdx.x * (kPrepThreads / 32));
@@ -61,6 +69,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const uint32_t* __rest
   // then let the fit kernel start its own prologue (which reads only what the scan launch wrote)
   pdl_wait();
   pdl_trigger();
+  sample_stamp(b, 0);
   // stage the first segment (one TMA bulk copy, signalled on an mbarrier) while the counts are totalled
   __shared__ __align__(8) uint64_t seg_bar;
   uint32_t seg_phase = 0;
@@ -90,8 +99,10 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const uint32_t* __rest
     if (lane == 0) { n_of[i] = n; counts[b * I + i] = (int32_t)n; }
   }
   __syncthreads();                              // n_of and the barrier's initialisation are visible
+  sample_stamp(b, 1);
   mbar_wait(&seg_bar, seg_phase);
   seg_phase ^= 1u;
+  sample_stamp(b, 2);
 
   // every variable below is uniform across the CTA
   int pos = 0;        // next unread word of the image's stream
@@ -179,6 +190,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const uint32_t* __rest
     }
     __syncthreads();      // end_pos / wtot are rewritten by the next pass
   }
+  sample_stamp(b, 3);
 }
 
 int auto_blocks(int I) {
@@ -218,6 +230,10 @@ int launch_sample(const uint32_t* chunk_counts, const PrepView& pv, int B, int I
 }
 
 }  // namespace la3d
+
+extern "C" void la3d_debug_sample_clocks(unsigned long long* clocks) {
+  cudaMemcpyToSymbol(la3d::g_sample_clocks, &clocks, sizeof(clocks));
+}
 
 extern "C" void la3d_set_mt_blocks(int n) { la3d::g_mt_blocks = n > 0 ? (n > 4096 ? 4096 : n) : 0; }
 
