@@ -22,6 +22,8 @@
 // No tensor cores: there is no dense contraction here.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "box_tail.cuh"
 #include "common.cuh"
 #include "prep.cuh"
@@ -34,7 +36,6 @@ namespace {
 constexpr int kThreads = 64;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxPts = 512;   // >= LA3D_SUBSAMPLE
-constexpr int kGroup = 8;      // samples per thread = ceil(500 / 64): all in flight together
 constexpr unsigned kFull = 0xffffffffu;
 
 struct FitArgs {
@@ -329,7 +330,12 @@ __device__ __forceinline__ void find_chunks(const uint32_t* pref, int chunks, in
 }
 
 // ---- the kernel ------------------------------------------------------------------------
-template <bool kScanned>
+// kGroup: samples per thread that move through the dependent loads of the gather together.  Measured on B200
+// (tools/fit_bench.py; 36-step sweep / pca / 360-step sweep / hull, us): 2048 images: 8 in flight 406 / 255 / 829 / 996,
+// 4: 390 / 233 / 796 / 924, 2: 381 / 248 / 759 / 874; 256 images: 8: 64 / 41 / 167 / 147, 4: 60 / 37 / 158 / 141,
+// 2: 59 / 35 / 160 / 140.  The gather is bound by sector throughput, not by latency, and fewer live registers help
+// everything after it.  launch_fit picks 2, or 4 for pca on launches of 8192 boxes or more; LA3D_FIT_GROUP overrides.
+template <bool kScanned, int kGroup>
 __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_raw[];
   __shared__ Smem sm;
@@ -598,13 +604,18 @@ int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s, bool pdl = 
     set_error("la3d fit: image or yaw sweep too large for shared memory (%zu bytes needed)", dyn + sizeof(Smem));
     return LA3D_EINVAL;
   }
-  if (scanned) {
-    if (dyn > 16 * 1024) LA3D_CUDA(cudaFuncSetAttribute(fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    LA3D_CUDA(launch_pdl(fit_kernel<true>, dim3((unsigned)nboxes), dim3(kThreads), dyn, s, pdl, a));
-  } else {
-    if (dyn > 16 * 1024) LA3D_CUDA(cudaFuncSetAttribute(fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    fit_kernel<false><<<nboxes, kThreads, dyn, s>>>(a);
-  }
+  static const int group_env = getenv("LA3D_FIT_GROUP") ? atoi(getenv("LA3D_FIT_GROUP")) : 0;
+  // measured choice (see the kernel): 2 samples in flight, except the pca method on many-wave launches
+  const int group = group_env ? group_env : (a.method == LA3D_METHOD_PCA && nboxes >= 8192 ? 4 : 2);
+  auto launch = [&](auto kernel) -> int {
+    if (dyn > 16 * 1024) LA3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    LA3D_CUDA(launch_pdl(kernel, dim3((unsigned)nboxes), dim3(kThreads), dyn, s, pdl && scanned, a));
+    return LA3D_OK;
+  };
+  int rc;
+  if (scanned) rc = group == 2 ? launch(fit_kernel<true, 2>) : group == 8 ? launch(fit_kernel<true, 8>) : launch(fit_kernel<true, 4>);
+  else rc = launch(fit_kernel<false, 4>);
+  if (rc) return rc;
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
 }
