@@ -605,8 +605,15 @@ int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s, bool pdl = 
     return LA3D_EINVAL;
   }
   static const int group_env = getenv("LA3D_FIT_GROUP") ? atoi(getenv("LA3D_FIT_GROUP")) : 0;
-  // measured choice (see the kernel): 2 samples in flight, except the pca method on many-wave launches
-  const int group = group_env ? group_env : (a.method == LA3D_METHOD_PCA && nboxes >= 8192 ? 4 : 2);
+  // measured choice (see the kernel): 2 samples in flight, except the pca method on many-wave launches; depth maps
+  // left in pinned HOST memory (the end-to-end path: 32-byte reads over PCIe, microseconds each) want all 8 in flight
+  bool host_depth = false;
+  if (scanned && a.depth) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, a.depth) == cudaSuccess) host_depth = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
+  const int group = group_env ? group_env : host_depth ? 8 : (a.method == LA3D_METHOD_PCA && nboxes >= 8192 ? 4 : 2);
   auto launch = [&](auto kernel) -> int {
     if (dyn > 16 * 1024) LA3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     LA3D_CUDA(launch_pdl(kernel, dim3((unsigned)nboxes), dim3(kThreads), dyn, s, pdl && scanned, a));
