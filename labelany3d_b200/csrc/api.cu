@@ -111,7 +111,6 @@ int sink_from_public(const la3d_sink* pub, RecordSink* out) {
       LA3D_REQUIRE(pub->flags[p] != nullptr, "null flag row");
       s.flags[p] = pub->flags[p];
     }
-    s.counter = pub->counter;
     s.status = pub->status;
     s.epoch = pub->epoch;
     s.rank = pub->rank;

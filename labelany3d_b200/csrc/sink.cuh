@@ -24,11 +24,9 @@ namespace la3d {
 struct RecordSink {
   void* out[LA3D_MAX_PEERS];          // record buffers: box j goes to out[p] + j * 64 elements, every p < n_out
   uint32_t* flags[LA3D_MAX_PEERS];    // flags[p] = rank p's flag row; flags[0] == nullptr: no peer synchronisation
-  uint32_t* counter;                  // unused since 0.2.1 (kept for the layout of la3d_sink)
   int32_t* status;                    // sticky error word (host-visible), set to 1 before a timeout trap
   unsigned long long timeout_ns;
   uint32_t epoch;
-  uint32_t total_ctas;                // CTAs (over all launches of the step) that count towards the release; 0 = this grid
   int n_out, rank, rec_f64;
 };
 
@@ -56,12 +54,6 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
-}
-// release-only increment: MEMBAR.ALL.SYS + ATOMG, no L1 invalidation (unlike __threadfence_system + atomicAdd)
-__device__ __forceinline__ uint32_t atom_add_release_sys(uint32_t* p, uint32_t v) {
-  uint32_t old;
-  asm volatile("atom.add.release.sys.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-  return old;
 }
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
