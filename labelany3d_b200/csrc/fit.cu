@@ -372,14 +372,19 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   const double* src_pts = nullptr;
   const uint32_t* cc = nullptr;
   if (kScanned) {
-    // exclusive prefix over the chunk totals; each thread owns a contiguous run.  (Keeping the quarter-count words
-    // in shared memory as well, to save the samples' scattered global load of them, measured 40 % slower on B200:
-    // more shared memory per CTA and more live registers in the gather loop.)
+    // exclusive prefix over the chunk totals.  The totals come in with COALESCED loads (thread t takes chunks t, t+64,
+    // ...) into the table itself; each thread then scans a contiguous run of the table in shared memory and writes
+    // the exclusive prefix back in place.  (Reading the contiguous runs straight from global memory, the first form,
+    // touched 32 sectors per warp load and read every word twice: at 1536 x 1536, 4608 chunks per plane, that was six
+    // times the sector requests of the whole sample gather.  Keeping the quarter-count words in shared memory as
+    // well measured 40 % slower: 2.4 KB more per CTA push the SM's carve-out to 228 KB and leave the L1 28 KB.)
     cc = a.chunk_counts + (size_t)box * a.chunks;
+    for (int c = tid; c < a.chunks; c += kThreads) pref[c] = __dp4a(__ldg(cc + c), 0x01010101u, 0u);
+    __syncthreads();
     const int per = (a.chunks + kThreads - 1) / kThreads;
     const int c_lo = min(tid * per, a.chunks), c_hi = min(c_lo + per, a.chunks);
     uint32_t run = 0;
-    for (int c = c_lo; c < c_hi; ++c) run = __dp4a(__ldg(cc + c), 0x01010101u, run);
+    for (int c = c_lo; c < c_hi; ++c) run += pref[c];
     uint32_t incl = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
     __syncthreads();
     uint32_t base = incl - run;
     for (int w = 0; w < warp; ++w) base += (uint32_t)sm.ired[w][0];
-    for (int c = c_lo; c < c_hi; ++c) { pref[c] = base; base = __dp4a(__ldg(cc + c), 0x01010101u, base); }
+    for (int c = c_lo; c < c_hi; ++c) { const uint32_t t = pref[c]; pref[c] = base; base += t; }
     if (tid == kThreads - 1) pref[a.chunks] = base;
     n_src = 0;
   } else {
