@@ -47,3 +47,28 @@ def test_split_step_in_a_cuda_graph(lib):
     replay()
     torch.cuda.synchronize()
     assert torch.equal(rec.view(torch.int64), want.view(torch.int64))
+
+
+def test_headline_batch_equals_its_shards():
+    """bench.py's headline workload on one GPU - 2048 images of 640 x 480 with 8 masks in ONE call - gives, bit for bit,
+    the records of the eight 256-image shards the 8-GPU run fits (image_offset = the shard's first image), all boxes
+    fitted, counts equal to the masks' pixel counts."""
+    from labelany3d_b200 import ops, synth
+    from oracle import la3d_oracle as orc
+    B, I, H, W = 2048, 8, 480, 640
+    depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=1236, device="cuda")
+    whole = ops.BoxFitter(B, I, H, W, out_dtype=torch.float32)(depth, K, masks, ground, "sweep", 36, seed=1234)
+    assert (whole[..., orc.O_STATUS] == 0).all()
+    counts = masks.view(B * I, -1).sum(dim=1).view(B, I).float()
+    assert torch.equal(whole[..., orc.O_NMASK], counts)
+    shard = ops.BoxFitter(256, I, H, W, out_dtype=torch.float32)
+    for r in range(8):
+        sl = slice(256 * r, 256 * (r + 1))
+        part = shard(depth[sl], K[sl], masks[sl], ground[sl], "sweep", 36, seed=1234, image_offset=256 * r)
+        assert torch.equal(part.view(torch.int32), whole[sl].contiguous().view(torch.int32)), r
+    # a sample against the oracle (the first two images)
+    d, k, m, g = (t[:2].cpu().numpy() for t in (depth, K, masks, ground))
+    want = orc.fit_boxes(d, k, m, g, "sweep", 36, seed=1234, impl="closed")
+    got = whole[:2].cpu().numpy().astype(np.float64)
+    ok = np.abs(got[..., :orc.O_YAW] - want[..., :orc.O_YAW]) <= np.maximum(1e-4, 1.2e-7 * np.abs(want[..., :orc.O_YAW]))
+    assert ok.all()
