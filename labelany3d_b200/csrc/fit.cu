@@ -7,8 +7,8 @@
 //      - scanned masks: rank r (the reference's random row of pts[mask]) -> binary
 //        search over the per-chunk prefix sums -> quarter of the chunk (packed byte
 //        counts) -> bit select in that quarter's 4 words -> pixel (v,u) -> depth gather
-//        -> exact lift (src/util.py:72 operation order); the eight samples of a thread
-//        move through that chain together, so a box pays four global round trips;
+//        -> exact lift (src/util.py:72 operation order); a few samples of a thread (kGroup,
+//        measured: 2 - 4) move through that chain together;
 //      - explicit points (the reference's own call pattern, util_3dbox.py:269-278).
 //   2. ground alignment p @ Rg, NaN-row filter (util_3dbox.py:128-143);
 //   3. yaw: PCA closed form | convex-hull edge search | uniform sweep.  Hull and sweep
