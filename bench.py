@@ -53,7 +53,7 @@ HOST_CEILING_NOTE = ("byte masks cross PCIe (~50 GB/s per GPU); all GPUs of the 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
