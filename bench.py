@@ -235,6 +235,7 @@ class Ctx:
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.dev = torch.device("cuda", self.local_rank)
         self.clocks = None
+        self._rendezvous = None
 
     def fence(self):
         self.torch.cuda.synchronize()
@@ -261,9 +262,14 @@ class Ctx:
         for _ in range(warmup):
             fn()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        self.fence()
         if clocks and self.clocks:
-            self.clocks.start()
+            self.clocks.start()          # before the fence: the poll thread is up when the ranks leave it
+        self.fence()
+        if self.world > 1:
+            # the ranks' host threads leave the fence tens of microseconds apart; a collective enqueued right before
+            # the start event makes every rank's STREAM wait for the slowest host, so the K steps are timed from a
+            # common device-side start (with the driver's K = 20 the host skew was ~10 us per step otherwise)
+            self.dist.all_reduce(self._rendezvous)
         a.record()
         for _ in range(steps):
             fn()
@@ -454,6 +460,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=cx.dev)
         dist.barrier()
+        cx._rendezvous = torch.zeros(1, device=cx.dev)
     else:
         __graft_entry__.build()
 
