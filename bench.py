@@ -396,11 +396,15 @@ def rle_leg(cx, depth, K, masks, ground, G, start, n, collective, steps, warmup)
     e2e_ms = cx.timed(e2e_step, e2e_steps, 2)
     if cx.world > 1:
         fitter.check_barrier_status()
-    h2d = h_counts.numel() * 4 + h_off.numel() * 8 + hK.numel() * 8 + hg.numel() * 8 + n * I * 500 * 32
+    # the in-place depth reads cross the bus as 128-byte line requests (tools/gather_ceiling.py): at most one per sample
+    h2d = h_counts.numel() * 4 + h_off.numel() * 8 + hK.numel() * 8 + hg.numel() * 8 + n * I * 500 * 128
     return {"value": G * I * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "runs_per_step_per_gpu": int(h_counts.numel()),
             "records_identical_to_byte_mask_path": same, "collective": collective,
             "e2e": {"value": G * I * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_rec.numel() * 4, "steps": e2e_steps},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_rec.numel() * 4, "steps": e2e_steps,
+                    "depth": "read in place from pinned host memory by the fit kernel, samples sorted by address so that "
+                             "lanes of a warp share 128-byte PCIe line requests (ceiling on this box: 343 M requests/s, "
+                             "profiles/r2_ae_gather_ceiling.json); h2d_bytes counts one line per sample (upper bound)"},
             "how": "masks of the same workload as COCO run-length annotations (column-major runs): la3d_fit_boxes_rle = "
                    "decode to bit planes (one CTA per plane, preparation CTAs in the same launch) -> subsample ranks -> fit"}
 

@@ -181,6 +181,13 @@ int la3d_sample_ranks(const uint32_t* chunk_counts, const void* prep, int B, int
 void la3d_debug_fit_clocks(long long* clocks);
 /* The same for the sampler: [images][4] globaltimer nanoseconds (start, counts totalled, words staged, ranks written). */
 void la3d_debug_sample_clocks(unsigned long long* clocks);
+/* Measurement aid (tools/gather_ceiling.py): ctas x 256 threads each issue `rounds` rounds of `inflight` (1, 2, 4, 8, 16)
+ * independent scattered 4-byte reads of src[0 .. n), every CTA inside its own `window` elements (window == n: anywhere);
+ * share > 1: that many neighbouring lanes read one 128-byte line, `spread` elements apart (address-sorted samples);
+ * out [ctas * 256] float receives the sums.  src may be device memory or pinned host memory: the latter measures the
+ * read-request rate the in-place depth gather of la3d_fit_boxes_rle can reach over PCIe.  Replaces nothing in the reference. */
+int la3d_debug_scatter_read(const float* src, size_t n, size_t window, int inflight, int rounds, int ctas, int share,
+                            int spread, float* out, la3d_stream_t stream);
 int la3d_fit_scanned(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,
                      const int32_t* ranks, int B, int I, int H, int W, int method, int yaw_steps, void* records,
                      int rec_f64, la3d_stream_t stream);

@@ -19,7 +19,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libla3d_sm100a.so")
 SOURCES = ["api.cu", "lift.cu", "mask_scan.cu", "mask_stats.cu", "sample.cu", "fit.cu", "project.cu",
-           "combine.cu", "median.cu", "rle.cu", "fit_all.cu", "align.cu"]
+           "combine.cu", "median.cu", "rle.cu", "fit_all.cu", "align.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -335,8 +335,16 @@ __device__ __forceinline__ void find_chunks(const uint32_t* pref, int chunks, in
 // 4: 390 / 233 / 796 / 924, 2: 381 / 248 / 759 / 874; 256 images: 8: 64 / 41 / 167 / 147, 4: 60 / 37 / 158 / 141,
 // 2: 59 / 35 / 160 / 140.  The gather is bound by sector throughput, not by latency, and fewer live registers help
 // everything after it.  launch_fit picks 2, or 4 for pca on launches of 8192 boxes or more; LA3D_FIT_GROUP overrides.
-template <bool kScanned, int kGroup>
+//
+// kSortDepth (depth maps left in pinned HOST memory, all samples of the box in one pass: kGroup * kThreads >= 512):
+// a scattered read over PCIe costs one 128-byte line request per distinct line per warp instruction, whatever the
+// loads in flight (tools/gather_ceiling.py: 343 M requests/s, 2x / 4x the samples when 2 / 4 lanes share a line).  The
+// box's pixel indices are therefore sorted (bitonic, in the footprint arrays, which are still free), consecutive
+// sorted samples are read by consecutive lanes, and the values return to sample order through shared memory - the
+// points, their order and every later operation are unchanged.
+template <bool kScanned, int kGroup, bool kSortDepth = false>
 __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
+  static_assert(!kSortDepth || (kScanned && kGroup * kThreads >= kMaxPts && kMaxPts == 512), "one pass over 512 samples");
   extern __shared__ __align__(16) unsigned char dyn_raw[];
   __shared__ Smem sm;
   double* areas = reinterpret_cast<double*>(dyn_raw);                               // [n_areas]
@@ -424,7 +432,9 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
   int n_valid = 0, inf_xz = 0, inf_y = 0;
   double y_lo = CUDART_INF, y_hi = -CUDART_INF;
   const int search_top = a.search_top;
-  for (int k0 = tid; k0 < nsel; k0 += kThreads * kGroup) {
+  // (kSortDepth: every thread runs the one pass, the block barriers of the sort sit inside it)
+  const int k_end = kSortDepth ? (nsel > 0 ? kMaxPts : 0) : nsel;
+  for (int k0 = tid; k0 < k_end; k0 += kThreads * kGroup) {
     double X[kGroup], Y[kGroup], Z[kGroup];
     if (kScanned) {
       uint32_t r[kGroup];
@@ -471,7 +481,45 @@ __global__ void __launch_bounds__(kThreads, 14) fit_kernel(FitArgs a) {
           word = next ? w[t + 1] : word;
         }
         p[j] = min(base_px[j] + wi * 32 + (int)__fns(word, 0, (int)rem[j] + 1), a.HW - 1);
-        d[j] = __ldg(a.depth + (size_t)img * a.HW + p[j]);
+        if (!kSortDepth) d[j] = __ldg(a.depth + (size_t)img * a.HW + p[j]);
+      }
+      if (kSortDepth) {
+        unsigned long long* keys = reinterpret_cast<unsigned long long*>(sm.x);   // [512] (pixel << 32 | sample)
+        float* dsh = reinterpret_cast<float*>(sm.z);                               // [512] depth by sample
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+          const int k = k0 + j * kThreads;
+          if (k < kMaxPts) keys[k] = k < nsel ? ((unsigned long long)(uint32_t)p[j] << 32) | (uint32_t)k : ~0ull;
+        }
+        __syncthreads();
+        for (int size = 2; size <= kMaxPts; size <<= 1) {
+          for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int t = tid; t < kMaxPts / 2; t += kThreads) {
+              const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1)), hi = lo | stride;
+              const unsigned long long ka = keys[lo], kb = keys[hi];
+              if ((ka > kb) == ((lo & size) == 0)) { keys[lo] = kb; keys[hi] = ka; }
+            }
+            __syncthreads();
+          }
+        }
+        unsigned long long key[kMaxPts / kThreads];
+#pragma unroll
+        for (int j = 0; j < kMaxPts / kThreads; ++j) key[j] = keys[j * kThreads + tid];
+        float got[kMaxPts / kThreads];
+#pragma unroll
+        for (int j = 0; j < kMaxPts / kThreads; ++j)
+          got[j] = key[j] != ~0ull ? __ldg(a.depth + (size_t)img * a.HW + (uint32_t)(key[j] >> 32)) : 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxPts / kThreads; ++j)
+          if (key[j] != ~0ull) dsh[(uint32_t)key[j] & (kMaxPts - 1)] = got[j];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+          const int k = k0 + j * kThreads;
+          d[j] = k < nsel ? dsh[k] : 0.f;
+        }
+        __syncthreads();                       // dsh / keys alias the footprint arrays written below
       }
 #pragma unroll
       for (int j = 0; j < kGroup; ++j) {
@@ -625,7 +673,9 @@ int launch_fit(bool scanned, FitArgs& a, int nboxes, cudaStream_t s, bool pdl = 
     return LA3D_OK;
   };
   int rc;
-  if (scanned) rc = group == 2 ? launch(fit_kernel<true, 2>) : group == 8 ? launch(fit_kernel<true, 8>) : launch(fit_kernel<true, 4>);
+  static const bool sort_env = !(getenv("LA3D_FIT_SORT_DEPTH") && atoi(getenv("LA3D_FIT_SORT_DEPTH")) == 0);
+  if (scanned && host_depth && group == 8 && sort_env) rc = launch(fit_kernel<true, 8, true>);
+  else if (scanned) rc = group == 2 ? launch(fit_kernel<true, 2>) : group == 8 ? launch(fit_kernel<true, 8>) : launch(fit_kernel<true, 4>);
   else rc = launch(fit_kernel<false, 4>);
   if (rc) return rc;
   LA3D_CUDA(cudaGetLastError());

@@ -437,10 +437,11 @@ def fit_boxes(depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, i
     The composed path of SURVEY.md section 3.4 for a batch: per instance the
     reference's ``estimate_bbox`` applied to ``depth_to_points(depth)[mask]`` plus the
     2D reprojection of the corners, with the legacy NumPy RNG re-seeded to
-    ``seed + image_offset + b`` at the start of image ``b``.
+    ``seed + image_offset + b`` at the start of image ``b``.  ``depth`` may stay in pinned host
+    memory (read in place; the masks decide the device).
     """
     B, I, H, W = masks.shape
-    return BoxFitter(B, I, H, W, device=depth.device, out_dtype=out_dtype)(
+    return BoxFitter(B, I, H, W, device=masks.device, out_dtype=out_dtype)(
         depth, K, masks, ground, method, yaw_steps, seed, image_offset).clone()
 
 

@@ -442,6 +442,27 @@ def test_full_size_other_configs(ops, cfg):
     check_record(r[sl], want, TOL_F64 * (10 if method == "pca" else 1), skip=(orc.O_NVALID,))
 
 
+@pytest.mark.parametrize("method,steps", [("pca", 0), ("convex_hull", 0), ("sweep", 36)])
+def test_depth_read_in_place_from_host_memory_is_bit_identical(ops, method, steps):
+    """Depth maps left in pinned host memory take the address-sorted gather (fit.cu, kSortDepth): the same records,
+    bit for bit, as with the depth in device memory - for empty masks, masks below one warp of samples, masks below
+    the 500-sample threshold (no draw) and large ones."""
+    from labelany3d_b200 import synth
+    B, I, H, W = 5, 6, 120, 200
+    depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=91, device="cuda", area=(0.05, 0.4))
+    masks[0, 0] = 0                                          # empty
+    masks[0, 1] = 0; masks[0, 1, 50, 60:71] = 1              # 11 pixels: fewer samples than threads
+    masks[1, 2] = 0; masks[1, 2, 30:45, 100:120] = 1         # 300 pixels: every pixel, in order
+    masks[2, 3] = 0; masks[2, 3, 10:11, 0:1] = 1             # a single pixel (PCA undefined)
+    masks[3, 4] = 1                                          # the whole image
+    depth[3, 7, 9] = float("nan"); depth[3, 8, 9] = float("inf")
+    want = ops.fit_boxes(depth, K, masks, ground, method, steps, seed=5, out_dtype=torch.float64).cpu().numpy()
+    host_depth = depth.cpu().pin_memory()
+    got = ops.fit_boxes(host_depth, K, masks, ground, method, steps, seed=5, out_dtype=torch.float64).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    assert (want[..., orc.O_STATUS] != 0).sum() >= 1 and (want[..., orc.O_STATUS] == 0).sum() >= 20
+
+
 @pytest.mark.parametrize("in_place", [True, False])
 def test_host_box_fitter_equals_the_device_path(ops, in_place):
     """Pinned host buffers in, pinned host records out (copy of batch k+1 under the kernels of batch k;
