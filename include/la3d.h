@@ -195,7 +195,11 @@ int la3d_fit_scanned(const float* depth, const void* prep, const uint32_t* bits,
 /* The four calls above as one pipeline of three launches on `stream`: the preparation rides in the
  * mask scan's launch (B extra CTAs at the front of its grid, so the latency-bound seeding hides
  * under the HBM-bound scan), then la3d_sample_ranks and la3d_fit_scanned.  `workspace` needs
- * la3d_fit_workspace_bytes() bytes, 256-byte aligned. */
+ * la3d_fit_workspace_bytes() bytes, 256-byte aligned.
+ * `depth` (here, in la3d_fit_scanned and in la3d_fit_boxes_rle) may be device memory or page-locked host memory
+ * mapped for the device: the fit reads only 500 values per box, so a host-resident map is read in place over
+ * PCIe, the samples of a box sorted by address so that the lanes of a warp share 128-byte line requests (same
+ * records; LA3D_FIT_SORT_DEPTH=0 switches the sort off). */
 /* Optional pipeline over parts of a batch (LA3D_PIPE_IMAGES=n or la3d_set_pipeline_images(n): n images per part,
  * 0 = never split = the default, -1 = back to the environment's choice): the scan of part p+1 on `stream` overlaps
  * the sampler and fit of part p on internal high-priority streams that fork from and join back into `stream`
