@@ -520,8 +520,8 @@ def main():
                "how": "ops.HostBoxFitter: masks / K / ground copied on a copy stream (two buffer sets, the copy of step "
                       "k+1 overlaps the kernels of step k), records copied back each step; depth "
                       + ("copied to the device each step" if args.e2e_copy_depth else
-                         "left in pinned host memory, 500 values per box gathered over PCIe by the fit kernel "
-                         "(counted as 32-byte sectors in h2d_bytes_per_step)")}
+                         "left in pinned host memory, 500 values per box read in place over PCIe by the fit kernel, sorted "
+                         "by address (counted as one 128-byte line request per sample in h2d_bytes_per_step: an upper bound)")}
         del hd, hK, hm, hg, host_rec, host_fit
 
     legs = {}

@@ -400,9 +400,10 @@ class HostBoxFitter:
         self.k = 0
 
     def h2d_bytes(self, B, I, H, W):
-        """Bytes that cross the bus host->device per call (gathered depth counted as 32-byte sectors)."""
+        """Bytes that cross the bus host->device per call (depth read in place: one 128-byte line request per
+        sample, an upper bound - address-sorted samples of a box share lines)."""
         copied = B * 72 + B * I * H * W + B * I * 24
-        return copied + (B * I * SUBSAMPLE * 32 if self.depth_in_place else B * H * W * 4)
+        return copied + (B * I * SUBSAMPLE * 128 if self.depth_in_place else B * H * W * 4)
 
     def __call__(self, depth, K, masks, ground, out_host, method="pca", yaw_steps=0, seed=0):
         for name, t in (("depth", depth), ("K", K), ("masks", masks), ("ground", ground), ("out_host", out_host)):
