@@ -47,6 +47,26 @@ def test_library_exports_every_header_symbol():
     assert _lib.load().la3d_fit_workspace_bytes(256, 8, 480, 640) > 256 * 8 * 9600 * 4
 
 
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """include/la3d.h compiles as strict C99 (no C++ or torch types in the boundary) and a C program links
+    against the shared library and gets versions, sizes and argument errors through it (examples/c_host.c)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "labelany3d_b200", "lib")
+    exe = str(tmp_path / "c_host")
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+           os.path.join(root, "examples", "c_host.c"), "-L", lib_dir, "-lla3d_sm100a", "-Wl,-rpath," + lib_dir, "-o", exe]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "la3d version" in run.stdout and "null pointers -> -1 (la3d_fit_boxes: null pointer)" in run.stdout
+
+
 def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
     """Argument checks come first in every entry point: null pointers / bad shapes return LA3D_EINVAL
     with a message naming the function, without a CUDA call (so this runs on the CPU box)."""
