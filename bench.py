@@ -479,10 +479,11 @@ def main():
         cx, G, I, H, W, w["method"], w["yaw_steps"], args.steps, warm, SEED, args.collective, verify=True, keep=True)
     boxes_per_step = G * I
 
-    # ---- per-kernel durations of this rank's block: the four kernels of a step issued one after the other on the
-    # current stream with CUDA events between them (in the headline pass the preparation rides in the scan's launch)
+    # ---- durations of the step's own three launches on this rank's block: the library records four CUDA events
+    # on the launching stream around them (la3d_debug_step_events): the scan WITH its preparation CTAs and its
+    # sparse bit-plane stores, the sampler, the fit - the same kernels the headline pass just ran
     single = fitter if world == 1 else fitter.local
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
 
     def step_events(ev):
         single(depth, K, masks, ground, w["method"], w["yaw_steps"], seed=1234, image_offset=start, events=ev)
@@ -497,10 +498,9 @@ def main():
     cx.fence()
     if cx.clocks:
         cx.clocks.stop()
-    k_prep = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
-    k_scan = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
-    k_samp = statistics.mean(e[2].elapsed_time(e[3]) for e in evs)
-    k_fit = statistics.mean(e[3].elapsed_time(e[4]) for e in evs)
+    k_scan = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+    k_samp = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    k_fit = statistics.mean(e[2].elapsed_time(e[3]) for e in evs)
 
     # ---- end to end through the public API: pinned host buffers -> boxes back on the host
     e2e = None
@@ -591,10 +591,11 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,
             "gather_verified": head.get("gather_verified"), "all_boxes_ok": head.get("all_boxes_ok"),
-            "kernels_ms": {"fit_prepare": k_prep, "mask_scan": k_scan, "sample_ranks": k_samp, "fit_boxes": k_fit,
+            "kernels_ms": {"mask_scan": k_scan, "sample_ranks": k_samp, "fit_boxes": k_fit,
                            "images": n,
-                           "how": "second timed pass of K steps over rank 0's block, the four kernels serialised on one stream "
-                                  "with CUDA events between them (in the headline pass fit_prepare is extra CTAs inside the scan's launch)"},
+                           "how": "second timed pass of K steps over rank 0's block through the same public call; the library "
+                                  "records CUDA events on the launching stream around the step's own three launches "
+                                  "(la3d_debug_step_events): the scan with the preparation CTAs in its grid, the sampler, the fit"},
             "roofline": {"kernel": "mask_scan_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic.get(f"mask_scan_kernel@{n}x{I}x{H}x{W}"),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": scan_bytes,

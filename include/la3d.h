@@ -181,6 +181,11 @@ int la3d_sample_ranks(const uint32_t* chunk_counts, const void* prep, int B, int
 void la3d_debug_fit_clocks(long long* clocks);
 /* The same for the sampler: [images][4] globaltimer nanoseconds (start, counts totalled, words staged, ranks written). */
 void la3d_debug_sample_clocks(unsigned long long* clocks);
+/* Measurement aid: 4 cudaEvent_t (or NULL to switch off).  While set, the fused steps (la3d_fit_boxes, la3d_fit_boxes_rle
+ * and their _to forms, unsplit) record them on the caller's stream before the first launch, after the scan / decode
+ * launch, after the sampler and after the fit: the durations of the step's OWN three launches without a profiler
+ * (bench.py's roofline).  Process-wide, not thread-safe. */
+void la3d_debug_step_events(void* const* events);
 /* Measurement aid (tools/gather_ceiling.py): ctas x 256 threads each issue `rounds` rounds of `inflight` (1, 2, 4, 8, 16)
  * independent scattered 4-byte reads of src[0 .. n), every CTA inside its own `window` elements (window == n: anywhere);
  * share > 1: that many neighbouring lanes read one 128-byte line, `spread` elements apart (address-sorted samples);

@@ -42,6 +42,7 @@ SIGNATURES = {
     "la3d_set_pipeline_images": (None, [_i]),
     "la3d_debug_fit_clocks": (None, [_vp]),
     "la3d_debug_sample_clocks": (None, [_vp]),
+    "la3d_debug_step_events": (None, [_vp]),
     "la3d_debug_scatter_read": (_i, [_vp, _sz, _sz, _i, _i, _i, _i, _i, _vp, _vp]),
     "la3d_fit_points": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "la3d_iou_matrix": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),

@@ -176,6 +176,8 @@ static PrepView prep_part(const PrepView& pv, int b0, int I) {
   return v;
 }
 
+static cudaEvent_t g_step_events[4] = {nullptr, nullptr, nullptr, nullptr};
+
 // `produce(b0, Bp, prep_args)` launches the pass that turns images [b0, b0 + Bp) into bit planes + quarter counts
 // (with the preparation CTAs of those images in its grid) on the caller's stream.
 template <typename Produce>
@@ -195,12 +197,19 @@ static int run_step(Produce&& produce, const float* depth, const double* K, cons
   if (parts > kMaxParts) parts = kMaxParts;
   if (parts <= 1) {
     const PrepArgs pa{K, ground, B, I, seed0, pv, pub};
+    cudaEvent_t* ev = g_step_events[0] ? g_step_events : nullptr;       // la3d_debug_step_events
+    if (ev) LA3D_CUDA(cudaEventRecord(ev[0], stream));
     int rc = produce(0, B, pa);
     if (rc) return rc;
+    if (ev) LA3D_CUDA(cudaEventRecord(ev[1], stream));
     rc = launch_sample(w.chunk_counts, pv, B, I, chunks, w.counts, w.ranks, stream, pdl_mode() == 1);
     if (rc) return rc;
-    return fit_scanned_sink(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, sink, stream,
-                            pdl_mode() != 0);
+    if (ev) LA3D_CUDA(cudaEventRecord(ev[2], stream));
+    rc = fit_scanned_sink(depth, w.prep, w.bits, w.chunk_counts, w.ranks, B, I, H, W, method, yaw_steps, sink, stream,
+                          pdl_mode() != 0);
+    if (rc) return rc;
+    if (ev) LA3D_CUDA(cudaEventRecord(ev[3], stream));
+    return LA3D_OK;
   }
   Pipe* pipe = nullptr;
   if (int rc = pipe_get(&pipe)) return rc;
@@ -250,7 +259,8 @@ static int fit_boxes_sink(const float* depth, const uint8_t* masks, const double
   // ground rotations) under it
   auto produce = [&](int b0, int Bp, const PrepArgs& pa) {
     const size_t p0 = (size_t)b0 * I;
-    return launch_mask_scan(masks + p0 * HW, Bp * I, H, W, mask_is_01, w.bits + p0 * words, w.chunk_counts + p0 * chunks, &pa, s);
+    // the workspace's bit planes are read by the fit's rank select only: chunks without set pixels are not stored
+    return launch_mask_scan(masks + p0 * HW, Bp * I, H, W, mask_is_01, w.bits + p0 * words, w.chunk_counts + p0 * chunks, &pa, s, true);
   };
   return run_step(produce, depth, K, ground, B, I, H, W, method, yaw_steps, seed + image_offset, w, sink, s);
 }
@@ -295,6 +305,10 @@ int publish_previous_epoch(const RecordSink& sink, cudaStream_t stream) {
   return LA3D_OK;
 }
 }  // namespace la3d
+
+extern "C" void la3d_debug_step_events(void* const* events) {
+  for (int i = 0; i < 4; ++i) la3d::g_step_events[i] = events ? static_cast<cudaEvent_t>(events[i]) : nullptr;
+}
 
 extern "C" void la3d_set_pipeline_images(int images_per_part) { la3d::g_pipe_override = images_per_part; }
 extern "C" void la3d_set_peer_timeout_ms(long long ms) { la3d::g_peer_timeout_ms = ms > 0 ? ms : 120000; }

@@ -57,7 +57,11 @@ __device__ __forceinline__ uint32_t pack16(uint4 q) {
   return acc;
 }
 
-template <bool k01, bool kVec, bool kPrep>
+// kSparse (the fused step only, whose bit planes live in its own workspace and are read by nothing but the fit
+// kernel's rank select): the bit words of a chunk without set pixels are not written - the select never lands in
+// such a chunk (its count is 0), and with masks covering a few percent of the image most of the bit planes'
+// bytes, 1/9 of the scan's DRAM traffic, are such zeros.
+template <bool k01, bool kVec, bool kPrep, bool kSparse = false>
 __global__ void __launch_bounds__(kThreads, kPrep ? 8 : 1)
     mask_scan_kernel(const uint8_t* __restrict__ masks, int HW, int chunks_per_plane, int tiles_per_plane,
                      uint32_t* __restrict__ bits, uint32_t* __restrict__ chunk_counts, PrepArgs pa) {
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, kPrep ? 8 : 1)
     const uint32_t other = __shfl_xor_sync(0xffffffffu, half, 1);
     // lanes 8q..8q+7 hold quarter q: one warp reduction yields all four byte counts
     const uint32_t quarters = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(half) << (8 * (lane >> 3)));
-    if ((lane & 1) == 0) dst_bits[c * kChunkWords + (lane >> 1)] = half | (other << 16);
+    if ((lane & 1) == 0 && (!kSparse || quarters != 0u)) dst_bits[c * kChunkWords + (lane >> 1)] = half | (other << 16);
     if (lane == 0) dst_cnt[c] = quarters;
   }
 }
@@ -231,8 +235,9 @@ static int launch_thin(const uint8_t* masks, int planes, int HW, int mask_is_01,
 }
 
 // prep == nullptr: the plain scan.  Otherwise prep->B extra CTAs at the front of the grid prepare the batch.
+// sparse_bits (needs prep): see kSparse.
 int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
-                     uint32_t* chunk_counts, const PrepArgs* prep, cudaStream_t s) {
+                     uint32_t* chunk_counts, const PrepArgs* prep, cudaStream_t s, bool sparse_bits) {
   LA3D_REQUIRE(masks && bits && chunk_counts, "null pointer");
   LA3D_REQUIRE(planes > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
@@ -249,12 +254,17 @@ int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is
   }
   dim3 grid((unsigned)ctas), block(kThreads);
   const PrepArgs pa = prep ? *prep : PrepArgs{};
+  static const bool sparse_env = !(getenv("LA3D_SCAN_SPARSE") && atoi(getenv("LA3D_SCAN_SPARSE")) == 0);
+  const bool sparse = sparse_bits && prep && sparse_env;
 #define LAUNCH(B01, VEC, PREP) \
   mask_scan_kernel<B01, VEC, PREP><<<grid, block, 0, s>>>(masks, HW, chunks, tiles, bits, chunk_counts, pa)
-#define LAUNCH2(B01, VEC) do { if (prep) LAUNCH(B01, VEC, true); else LAUNCH(B01, VEC, false); } while (0)
+#define LAUNCH_SPARSE(B01, VEC) \
+  mask_scan_kernel<B01, VEC, true, true><<<grid, block, 0, s>>>(masks, HW, chunks, tiles, bits, chunk_counts, pa)
+#define LAUNCH2(B01, VEC) do { if (prep && sparse) LAUNCH_SPARSE(B01, VEC); else if (prep) LAUNCH(B01, VEC, true); else LAUNCH(B01, VEC, false); } while (0)
   if (mask_is_01) { if (vec) LAUNCH2(true, true); else LAUNCH2(true, false); }
   else            { if (vec) LAUNCH2(false, true); else LAUNCH2(false, false); }
 #undef LAUNCH2
+#undef LAUNCH_SPARSE
 #undef LAUNCH
   LA3D_CUDA(cudaGetLastError());
   return LA3D_OK;
@@ -264,7 +274,7 @@ int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is
 extern "C" int la3d_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
                               uint32_t* chunk_counts, la3d_stream_t stream) {
   return la3d::launch_mask_scan(masks, planes, H, W, mask_is_01, bits, chunk_counts, nullptr,
-                                static_cast<cudaStream_t>(stream));
+                                static_cast<cudaStream_t>(stream), false);
 }
 
 extern "C" int la3d_mask_scan_thin(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,

@@ -163,7 +163,7 @@ __device__ __forceinline__ void prep_body(const PrepArgs& pa, int first, uint32_
 }
 
 int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is_01, uint32_t* bits,
-                     uint32_t* chunk_counts, const PrepArgs* prep, cudaStream_t s);
+                     uint32_t* chunk_counts, const PrepArgs* prep, cudaStream_t s, bool sparse_bits = false);
 
 int launch_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes, int H, int W, int max_runs,
                       uint32_t* ends_ws, uint32_t* bits, uint32_t* chunk_counts, int32_t* status, const PrepArgs* prep,

@@ -281,10 +281,11 @@ class BoxFitter:
     def __call__(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0, out=None,
                  events=None, sink=None):
         """Fit every (image, instance) box; returns ``records[B,I,64]`` (a buffer owned by the plan
-        unless ``out`` is given).  ``events``: optional list of 5 ``torch.cuda.Event``; the four kernels
-        are then issued one after the other on the current stream (no overlap) with the events
-        recorded before, between and after them: prepare, scan, sample, fit (per-kernel timing
-        without a profiler).  ``sink``: a ``_lib.Sink`` (``la3d_sink``): the fit kernel then writes every
+        unless ``out`` is given).  ``events``: optional list of ``torch.cuda.Event``.  Four: recorded by the
+        library around the step's own three launches (before, after the scan with its preparation CTAs, after
+        the sampler, after the fit).  Five: the four kernels are issued one after the other through the
+        step-wise entry points with the events recorded before, between and after them: prepare, scan,
+        sample, fit.  (Per-kernel timing without a profiler.)  ``sink``: a ``_lib.Sink`` (``la3d_sink``): the fit kernel then writes every
         record to all its destinations, e.g. this rank's slot in the peer-mapped gathered buffer of every
         rank, and synchronises with the peers itself (``la3d_fit_boxes_to``) instead of writing ``out``."""
         B, I, H, W = self.shape
@@ -315,11 +316,18 @@ class BoxFitter:
                                            int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace), self.ws_bytes,
                                            ctypes.byref(sink), st)
                 _lib.check(rc, "la3d_fit_boxes_to")
-            elif events is None:
-                rc = lib.la3d_fit_boxes(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01,
-                                        _method_id(method), int(yaw_steps), int(seed) & 0xFFFFFFFF,
-                                        int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace), self.ws_bytes,
-                                        _ptr(rec), f64, st)
+            elif events is None or len(events) == 4:
+                if events is not None:
+                    # the step's own three launches, timed from inside the call (la3d_debug_step_events)
+                    for e in events:
+                        e.record()                # torch creates the CUDA event lazily, on the first record
+                    handles = (ctypes.c_void_p * 4)(*[e.cuda_event for e in events])
+                    lib.la3d_debug_step_events(handles)
+                try:
+                    rc = self._fit_boxes(lib, depth, m8, K, ground, is01, method, yaw_steps, seed, image_offset, rec, f64, st)
+                finally:
+                    if events is not None:
+                        lib.la3d_debug_step_events(None)
                 _lib.check(rc, "la3d_fit_boxes")
             else:
                 # the same kernels through the step-wise entry points, serialised, with events in between
@@ -336,6 +344,13 @@ class BoxFitter:
                                                 int(yaw_steps), _ptr(rec), f64, st), "la3d_fit_scanned")
                 events[4].record()
         return rec
+
+    def _fit_boxes(self, lib, depth, m8, K, ground, is01, method, yaw_steps, seed, image_offset, rec, f64, st):
+        B, I, H, W = self.shape
+        return lib.la3d_fit_boxes(_ptr(depth), _ptr(m8), _ptr(K), _ptr(ground), B, I, H, W, is01,
+                                  _method_id(method), int(yaw_steps), int(seed) & 0xFFFFFFFF,
+                                  int(image_offset) & 0xFFFFFFFF, _ptr(self.workspace), self.ws_bytes,
+                                  _ptr(rec), f64, st)
 
     def capture(self, depth, K, masks, ground=None, method="pca", yaw_steps=0, seed=0, image_offset=0, out=None):
         """Record one call as a CUDA graph and return its ``replay()``: the kernels of a step (and

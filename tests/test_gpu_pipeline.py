@@ -72,3 +72,27 @@ def test_headline_batch_equals_its_shards():
     got = whole[:2].cpu().numpy().astype(np.float64)
     ok = np.abs(got[..., :orc.O_YAW] - want[..., :orc.O_YAW]) <= np.maximum(1e-4, 1.2e-7 * np.abs(want[..., :orc.O_YAW]))
     assert ok.all()
+
+
+def test_sparse_bit_planes_and_in_step_events(lib):
+    """The fused step does not store the bit words of chunks without set pixels (its workspace is read by the rank
+    select only): the records equal those of the step-wise entry points (dense bit planes) bit for bit, also when
+    the SAME workspace is reused for masks that empty chunks a previous call filled; and the four events the
+    library records around the step's own launches (la3d_debug_step_events) come out ordered."""
+    from labelany3d_b200 import ops, synth
+    B, I, H, W = 6, 4, 128, 256
+    fit = ops.BoxFitter(B, I, H, W)
+    for seed, area in ((31, (0.2, 0.6)), (32, (0.02, 0.06)), (33, (0.05, 0.3))):      # large masks first, then small ones
+        depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=seed, device="cuda", area=area)
+        if seed == 32:
+            masks[1] = 0                                                               # a whole image without masks
+        five = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        want = ops.BoxFitter(B, I, H, W)(depth, K, masks, ground, "sweep", 36, seed=3, events=five).clone()
+        four = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        got = fit(depth, K, masks, ground, "sweep", 36, seed=3, events=four).clone()
+        plain = fit(depth, K, masks, ground, "sweep", 36, seed=3).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(got.view(torch.int64), want.view(torch.int64)), seed
+        assert torch.equal(plain.view(torch.int64), want.view(torch.int64)), seed
+        spans = [four[i].elapsed_time(four[i + 1]) for i in range(3)]
+        assert all(s > 0 for s in spans), spans
