@@ -403,7 +403,7 @@ static int fit_boxes_rle_sink(const float* depth, const uint32_t* run_counts, co
   auto produce = [&](int b0, int Bp, const PrepArgs& pa) {
     const size_t p0 = (size_t)b0 * I;
     return launch_rle_decode(run_counts, run_offsets + p0, Bp * I, H, W, max_runs, ends_ws, w.bits + p0 * words,
-                             w.chunk_counts + p0 * chunks, rle_status + p0, &pa, s);
+                             w.chunk_counts + p0 * chunks, rle_status + p0, &pa, s, true);
   };
   return run_step(produce, depth, K, ground, B, I, H, W, method, yaw_steps, seed + image_offset, w, sink, s);
 }

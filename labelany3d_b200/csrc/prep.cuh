@@ -167,7 +167,7 @@ int launch_mask_scan(const uint8_t* masks, int planes, int H, int W, int mask_is
 
 int launch_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes, int H, int W, int max_runs,
                       uint32_t* ends_ws, uint32_t* bits, uint32_t* chunk_counts, int32_t* status, const PrepArgs* prep,
-                      cudaStream_t s);
+                      cudaStream_t s, bool sparse_bits = false);
 
 struct RecordSink;
 int fit_scanned_sink(const float* depth, const void* prep, const uint32_t* bits, const uint32_t* chunk_counts,

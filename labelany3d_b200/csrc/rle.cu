@@ -44,6 +44,8 @@ struct RleArgs {
   uint32_t* ends_ws;           // nullable [total runs]: run ends of planes that do not fit shared memory
   int H, W, HW, chunks, smem_runs, stage_words;   // stage_words: staging tile per warp (0 on the fast path)
   int fast;                    // W % 128 == 0 and 16-byte aligned bit planes: rows and quarters never straddle words
+  int sparse;                  // bands without a set pixel are not written (fused step: the planes are read by the
+                               // fit's rank select only, which never lands in a chunk whose count is 0)
   uint32_t* bits;
   uint32_t* chunk_counts;
   int32_t* status;
@@ -184,6 +186,14 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) rle_decode_kernel(RleArgs 
     const int nrows = y0_ll >= H ? 0 : min(32, H - (int)y0_ll);
     const int y0 = (int)min(y0_ll, (long long)H);
     if (nrows == 0 || x_hi < x_lo || y0 > y_hi || y0 + nrows - 1 < y_lo) {   // nothing set in these rows
+      if (a.sparse) {
+        // only the words of chunks (16 words) this band shares with a neighbouring band: that one may hold pixels
+        const long long hi = w_base + n_words;
+        const long long head_end = min(hi, (w_base + 15) & ~15ll), tail_beg = max(head_end, hi & ~15ll);
+        for (long long wi = w_base + lane; wi < head_end; wi += 32) out_bits[wi] = 0u;
+        for (long long wi = tail_beg + lane; wi < hi; wi += 32) out_bits[wi] = 0u;
+        continue;
+      }
       if (a.fast) {
         uint4* z = reinterpret_cast<uint4*>(out_bits + w_base);
         for (int i = lane; i < (n_words >> 2); i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) rle_decode_kernel(RleArgs 
 // prep == nullptr: the plain decode.  Otherwise ceil(prep->B / 8) extra CTAs at the front of the grid prepare the batch.
 int launch_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes, int H, int W, int max_runs,
                       uint32_t* ends_ws, uint32_t* bits, uint32_t* chunk_counts, int32_t* status, const PrepArgs* prep,
-                      cudaStream_t s) {
+                      cudaStream_t s, bool sparse_bits) {
   LA3D_REQUIRE(counts && offsets && bits && chunk_counts && status, "null pointer");
   LA3D_REQUIRE(planes > 0 && H > 0 && W > 0, "non-positive shape");
   LA3D_REQUIRE((long long)H * W < (1ll << 30), "image too large");
@@ -291,6 +301,8 @@ int launch_rle_decode(const uint32_t* counts, const int64_t* offsets, int planes
   a.H = H; a.W = W; a.HW = H * W; a.chunks = (int)la3d_chunks_per_plane(H, W);
   a.bits = bits; a.chunk_counts = chunk_counts; a.status = status;
   a.fast = (W % 128 == 0) && aligned16(bits);
+  static const bool sparse_env = !(getenv("LA3D_SCAN_SPARSE") && atoi(getenv("LA3D_SCAN_SPARSE")) == 0);
+  a.sparse = sparse_bits && prep && sparse_env;
   // shared memory: a staging tile per warp, the per-column run table, and the run ends if they fit beside them
   const int P = ((W + 31) >> 5) | 1;
   a.stage_words = a.fast ? 0 : 32 * P;

@@ -74,6 +74,29 @@ def test_headline_batch_equals_its_shards():
     assert ok.all()
 
 
+@pytest.mark.parametrize("H,W", [(128, 256), (120, 200), (97, 131)])
+def test_sparse_bit_planes_from_run_lengths(lib, H, W):
+    """The fused run-length step leaves bands of 32 rows without a set pixel unwritten (except the words of chunks
+    shared with a neighbouring band): same records as from dense planes, with one plan reused across batches whose
+    masks move, for widths whose bands do and do not end on chunk boundaries."""
+    from labelany3d_b200 import coco_rle, ops, synth
+    B, I = 5, 4
+    plan = None
+    for seed, area in ((41, (0.3, 0.7)), (42, (0.03, 0.08)), (43, (0.05, 0.3)), (44, (0.03, 0.08))):
+        depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=seed, device="cuda", area=area)
+        if seed == 42:
+            masks[2] = 0
+        counts, offsets, max_runs = coco_rle.runs_from_masks_device(masks.reshape(-1, H, W))
+        if plan is None:
+            plan = ops.RleBoxFitter(B, I, H, W, 4 * counts.numel() + 64, 4 * max_runs + 64)
+            plan.workspace.fill_(0xA5)                       # stale bytes where nothing gets written
+        bits, cc, status = ops.rle_decode(counts, offsets, H, W, max_runs)          # dense planes
+        assert not bool(status.any())
+        want = ops.fit_boxes_bits(depth, K, bits, cc, I, ground, "convex_hull", 0, seed=9)
+        got = plan(depth, K, counts, offsets, ground, "convex_hull", 0, seed=9)
+        assert torch.equal(got.view(torch.int64), want.view(torch.int64)), seed
+
+
 def test_sparse_bit_planes_and_in_step_events(lib):
     """The fused step does not store the bit words of chunks without set pixels (its workspace is read by the rank
     select only): the records equal those of the step-wise entry points (dense bit planes) bit for bit, also when
@@ -82,6 +105,7 @@ def test_sparse_bit_planes_and_in_step_events(lib):
     from labelany3d_b200 import ops, synth
     B, I, H, W = 6, 4, 128, 256
     fit = ops.BoxFitter(B, I, H, W)
+    fit.workspace.fill_(0xA5)                                # stale bytes where nothing gets written
     for seed, area in ((31, (0.2, 0.6)), (32, (0.02, 0.06)), (33, (0.05, 0.3))):      # large masks first, then small ones
         depth, K, masks, ground = synth.make_inputs(B, H, W, I, seed=seed, device="cuda", area=area)
         if seed == 32:
