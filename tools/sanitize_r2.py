@@ -44,6 +44,21 @@ assert int(m2.view(2, -1).sum(1).min()) > 2048
 for method, steps in (("convex_hull", 0), ("sweep", 12)):
     rec = ops.fit_boxes_all(d2, K2, m2, g2, method=method, yaw_steps=steps)
     assert (rec[..., 41] == 0).all()
+# depth left in pinned host memory: the address-sorted in-place gather (sort in the footprint arrays); masks with
+# fewer samples than threads and an empty one; then the sparse bit-plane stores with a reused, stale workspace
+m3 = masks.clone()
+m3[0, 0] = 0
+m3[0, 1] = 0; m3[0, 1, 40, 30:41] = 1
+host_depth = depth.cpu().pin_memory()
+for method, steps in (("pca", 0), ("convex_hull", 0), ("sweep", 12)):
+    got = ops.fit_boxes(host_depth, K, m3, ground, method, steps, seed=2)
+    assert torch.equal(got.view(torch.int64), ops.fit_boxes(depth, K, m3, ground, method, steps, seed=2).view(torch.int64))
+plan = ops.BoxFitter(B, I, H, W)
+plan.workspace.fill_(0xA5)
+for mm in (masks, m3, masks):
+    five = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    dense = ops.BoxFitter(B, I, H, W)(depth, K, mm, ground, "sweep", 12, seed=2, events=five).clone()
+    assert torch.equal(plan(depth, K, mm, ground, "sweep", 12, seed=2).view(torch.int64), dense.view(torch.int64))
 # lift with the in-kernel camera (f32 / f64)
 ops.depth_lift(depth, K, out_dtype=torch.float32)
 ops.depth_lift(depth, K, out_dtype=torch.float64)
