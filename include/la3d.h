@@ -154,6 +154,10 @@ size_t la3d_prep_bytes(int B, int I);
 int la3d_fit_prepare(const double* K, const double* ground, int B, int I, uint32_t seed, uint32_t image_offset,
                      void* prep, size_t prep_bytes, la3d_stream_t stream);
 void la3d_set_mt_blocks(int n);
+/* Tuning hook: blocks of 624 words a sampler CTA stages in shared memory at a time (1 .. 16; 0 = the library's
+ * choice).  Fewer blocks = less shared memory per CTA = more resident CTAs, at the price of refills; results
+ * never depend on it. */
+void la3d_set_sample_seg_blocks(int n);
 
 /* ---------------------------------------------------------------------------
  * Per-image subsample ranks.  Replaces `np.random.randint(0, N, 500)` of

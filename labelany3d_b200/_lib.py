@@ -26,6 +26,7 @@ SIGNATURES = {
     "la3d_prep_bytes": (_sz, [_i, _i]),
     "la3d_fit_prepare": (_i, [_vp, _vp, _i, _i, _u32, _u32, _vp, _sz, _vp]),
     "la3d_set_mt_blocks": (None, [_i]),
+    "la3d_set_sample_seg_blocks": (None, [_i]),
     "la3d_sample_ranks": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "la3d_fit_scanned": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "la3d_fit_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -39,6 +39,7 @@ constexpr int kSegBlocksMax = 16;          // words staged in shared memory at a
 constexpr unsigned kFull = 0xffffffffu;
 
 int g_mt_blocks = 0;                       // 0 = automatic (la3d_set_mt_blocks)
+int g_seg_blocks = 0;                      // 0 = automatic (la3d_set_sample_seg_blocks)
 __device__ unsigned long long* g_sample_clocks = nullptr;   // debug: [images][4] globaltimer stamps (la3d_debug_sample_clocks)
 __device__ __forceinline__ void sample_stamp(int b, int i) {
   if (g_sample_clocks && threadIdx.x == 0) {
@@ -218,9 +219,16 @@ PrepView prep_view(void* base, int B, int I, int nblk) {
 
 int prep_blocks(int I) { return auto_blocks(I); }
 
+// Blocks of 624 words a sampler CTA stages in shared memory at a time (it refills when they are used up).
+static int seg_blocks(int B) {
+  (void)B;
+  if (g_seg_blocks > 0) return g_seg_blocks < kSegBlocksMax ? g_seg_blocks : kSegBlocksMax;
+  return kSegBlocksMax;
+}
+
 int launch_sample(const uint32_t* chunk_counts, const PrepView& pv, int B, int I, int chunks, int32_t* counts,
                   int32_t* ranks, cudaStream_t s, bool pdl, int b0) {
-  const int seg_cap = (pv.nblk < kSegBlocksMax ? pv.nblk : kSegBlocksMax) * kMtN;
+  const int seg_cap = (pv.nblk < seg_blocks(B) ? pv.nblk : seg_blocks(B)) * kMtN;
   const size_t dyn = ((size_t)seg_cap + I) * 4;
   if (dyn > 48 * 1024)
     LA3D_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -234,6 +242,8 @@ int launch_sample(const uint32_t* chunk_counts, const PrepView& pv, int B, int I
 extern "C" void la3d_debug_sample_clocks(unsigned long long* clocks) {
   cudaMemcpyToSymbol(la3d::g_sample_clocks, &clocks, sizeof(clocks));
 }
+
+extern "C" void la3d_set_sample_seg_blocks(int n) { la3d::g_seg_blocks = n > 0 ? n : 0; }
 
 extern "C" void la3d_set_mt_blocks(int n) { la3d::g_mt_blocks = n > 0 ? (n > 4096 ? 4096 : n) : 0; }
 
